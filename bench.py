@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py — DLRM-RMC1 inferences/s on B200 through the accel hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path (lengths->offsets already staged, bottom
+MLP, K1 multi-table SparseLengthsSum gather + cat interaction, top MLP) over one
+batch of ``--batch`` synthetic RMC1 samples (default 16384 = 16 coalesced
+1024-item queries; reference shape: models/configs/dlrm_rm1.json,
+data_generator/dlrm_data_caffe2.py).  Tables (4.1 GB) are far larger than the
+126 MB L2 and every step reads a different staged batch, so no L2 flush is
+needed between timed iterations ("inputs larger than L2").
+
+Prints ONE JSON line (see the keys at the bottom).  ``value`` is measured with
+the inputs resident in HBM; ``e2e`` goes through the C-ABI with pinned HOST
+buffers (H2D of ids/lengths/dense and D2H of the scores inside the timed
+region); ``roofline`` is the K1 gather kernel timed with CUDA events on the
+engine's stream inside the timed region; ``cpu_baseline`` is the torch-CPU port
+of the reference's CPU engine timed on this box's host cores.
+"""
+from __future__ import absolute_import, division, print_function
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "rm1": "dlrm_rm1.json", "rm2": "dlrm_rm2.json", "rm3": "dlrm_rm3.json",
+    "wnd": "wide_and_deep.json", "ncf": "ncf.json", "din": "din.json",
+}
+METRIC = "DLRM-RMC1 inferences/sec"
+UNIT = "inferences/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    p.add_argument("--config", type=str, default="rm1", choices=sorted(CONFIGS))
+    p.add_argument("--batch", type=int, default=16384, help="samples per step")
+    p.add_argument("--staged_batches", type=int, default=4)
+    p.add_argument("--precision", type=str, default="fp32")
+    p.add_argument("--interaction", type=str, default=None, help="override: cat | dot")
+    p.add_argument("--cpu_seconds", type=float, default=10.0)
+    p.add_argument("--cpu_sample", type=int, default=4096)
+    p.add_argument("--no_cpu_baseline", action="store_true")
+    p.add_argument("--no_sweep", action="store_true")
+    p.add_argument("--no_e2e", action="store_true")
+    p.add_argument("--seed", type=int, default=123)
+    return p.parse_args()
+
+
+def model_args(opts, batch, num_batches):
+    from deeprecsys_b200.utils.utils import cli
+    cfg = os.path.join(ROOT, "deeprecsys_b200", "models", "configs", CONFIGS[opts.config])
+    argv = ["--config_file", cfg, "--num_batches", str(num_batches),
+            "--max_mini_batch_size", str(batch), "--numpy_rand_seed", str(opts.seed)]
+    a = cli(argv)
+    if opts.interaction:
+        a.arch_interaction_op = opts.interaction
+    return a
+
+
+def synth_tables(spec, seed):
+    """Random-init tables of the reference's distribution U(+-sqrt(1/n)), drawn in
+    float32 with a fast generator (bench only; the engine's drop-in path uses the
+    reference's exact legacy-RNG draws, deeprecsys_b200/spec.py)."""
+    rng = np.random.default_rng(seed)
+    for t, rows in enumerate(spec.table_rows):
+        W = rng.random((rows, spec.D), dtype=np.float32)
+        bound = np.float32(np.sqrt(1.0 / rows))
+        W *= 2 * bound
+        W -= bound
+        yield t, W
+
+
+def synth_fcs(spec, seed):
+    from deeprecsys_b200.spec import draw_fc
+    np.random.seed(seed + 1)
+    fcs = {}
+    for mlp_id, ln in spec.mlps:
+        for layer in range(len(ln) - 1):
+            fcs[(mlp_id, layer)] = draw_fc(ln[layer], ln[layer + 1])
+    return fcs
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------
+def run_reference(opts):
+    """--impl reference: the reference's CPU path (torch-CPU port of
+    inferenceEngine.py's net; Caffe2 itself is not importable here) on the host
+    cores, same workload shape, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
+    from deeprecsys_b200.spec import ModelSpec
+    from oracle.torch_cpu_engine import TorchCpuModel
+    n = int(opts.cpu_sample)
+    a = model_args(opts, n, 1)
+    spec = ModelSpec(a)
+    _, lX, lS_l, lS_i = DLRMDataGenerator(a).generate_input_data()
+    tables = [W for _, W in synth_tables(spec, opts.seed)]
+    model = TorchCpuModel(spec, tables, synth_fcs(spec, opts.seed))
+    dense = lX[0] if spec.m_den > 0 else None
+    ids = [torch.as_tensor(lS_i[0][t], dtype=torch.int64) for t in range(spec.T)]
+    lengths = [lS_l[0][t] for t in range(spec.T)]
+    for _ in range(max(1, opts.warmup)):
+        model.forward(dense, ids, lengths)
+    t0 = time.perf_counter()
+    for _ in range(opts.steps):
+        model.forward(dense, ids, lengths)
+    dt = time.perf_counter() - t0
+    value = n * opts.steps / dt
+    cores = torch.get_num_threads()
+    sample = "%d steps x %d samples of the %s workload" % (opts.steps, n, opts.config)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
+        "ms_per_step": 1e3 * dt / opts.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dlrm_%s cat, %d samples/step (bounded CPU sample)"
+                   % (opts.config, n)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample,
+                         "what": "torch-CPU port of inferenceEngine.py net "
+                                 "(embedding_bag + addmm/MKL); caffe2 not importable"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores_available": len(os.sched_getaffinity(0)),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(opts):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
+    from deeprecsys_b200.engine import AccelEngine, pinned_empty
+    from deeprecsys_b200.spec import ModelSpec
+
+    B, nb = int(opts.batch), int(opts.staged_batches)
+    a = model_args(opts, B, nb)
+    spec = ModelSpec(a)
+    eng = AccelEngine(args=a, device=local, max_batch=B, precision=opts.precision)
+    keep_host = (rank == 0 and world == 1 and not opts.no_cpu_baseline)
+    host_tables = []
+    for t, W in synth_tables(spec, opts.seed + 1000 * rank):
+        eng.load_table(t, W)
+        if keep_host:
+            host_tables.append(W)
+    fcs = synth_fcs(spec, opts.seed)
+    for (mlp_id, layer), (W, b) in fcs.items():
+        eng.load_fc(mlp_id, layer, W, b)
+
+    np.random.seed(opts.seed + rank)
+    _, lX, lS_l, lS_i = DLRMDataGenerator(a).generate_input_data()
+    for j in range(nb):
+        eng.stage_batch(j, lX[j] if spec.m_den > 0 else None,
+                        [lS_i[j][t] for t in range(spec.T)], [lS_l[j][t] for t in range(spec.T)])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: inputs resident in HBM, device-timed
+    for i in range(max(3, opts.warmup)):
+        eng.enqueue_staged(i % nb, B)
+    eng.sync()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    eng.sync()
+    eng.profile_begin(opts.steps)
+    eng.timer_start()
+    for i in range(opts.steps):
+        eng.enqueue_staged(i % nb, B)
+    ms_total = eng.timer_stop()
+    eng.sync()
+    barrier()
+    clocks = sampler.stop()
+    n_prof, pre_ms, gather_ms, post_ms = eng.profile_end()
+    launches = eng.launch_count() - launches0
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / opts.steps
+    value = world * B * opts.steps / (ms_total * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (K1 gather), same timed region
+    peak, peak_src = load_peaks()
+    bytes_per_sample = spec.gather_bytes_per_sample(fused=True)
+    gather_ms_avg = gather_ms / max(1, n_prof)
+    achieved = bytes_per_sample * B / (gather_ms_avg * 1e-3) / 1e9 if gather_ms_avg > 0 else 0.0
+    roofline = {
+        "kernel": "k_sls_gather (multi-table SparseLengthsSum + cat layout)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0, "traffic": None,
+        "peak_source": peak_src, "alg_bytes_per_sample": bytes_per_sample,
+        "kernel_ms_avg": gather_ms_avg,
+        "step_share": {"pre_gather_mlp": pre_ms / max(1e-9, pre_ms + gather_ms + post_ms),
+                       "gather": gather_ms / max(1e-9, pre_ms + gather_ms + post_ms),
+                       "post_gather_mlp": post_ms / max(1e-9, pre_ms + gather_ms + post_ms)},
+    }
+
+    # ---------------- e2e: C-ABI with pinned HOST buffers, H2D + D2H inside
+    e2e, latency = None, None
+    if not opts.no_e2e:
+        T, L = spec.T, spec.L
+        h_idx, _k1 = pinned_empty((T, B * L), np.int32)
+        h_len, _k2 = pinned_empty((T, B), np.int32)
+        h_den, _k3 = pinned_empty((B, max(1, spec.m_den)), np.float32)
+        h_out, _k4 = pinned_empty((B, spec.out_dim), np.float32)
+        h_idx[:] = lS_i[0]; h_len[:] = lS_l[0]
+        if spec.m_den > 0:
+            h_den[:] = lX[0]
+        idx_ptrs = (C.c_void_p * T)(*[h_idx[t].ctypes.data for t in range(T)])
+        len_ptrs = (C.c_void_p * T)(*[h_len[t].ctypes.data for t in range(T)])
+        den_ptr = C.c_void_p(h_den.ctypes.data) if spec.m_den > 0 else None
+        out_ptr = C.c_void_p(h_out.ctypes.data)
+
+        def e2e_step(bs):
+            eng.enqueue_host(den_ptr, idx_ptrs, 0, len_ptrs, bs, out_ptr)
+            eng.sync()
+
+        for _ in range(max(3, opts.warmup)):
+            e2e_step(B)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(opts.steps):
+            e2e_step(B)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        h2d = B * (T * L * 4 + T * 4 + spec.m_den * 4)
+        d2h = B * spec.out_dim * 4
+        e2e = {"value": world * B * opts.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * dt / opts.steps, "ids_dtype": "int32",
+               "note": "sequential H2D -> kernels -> D2H per step, wall clock, max over ranks"}
+        # per-query latency at the reference's largest query size (1024), same path.
+        # NOTE: the first 1024 samples of the staged host batch (inferenceEngine.py:200-215)
+        q = min(1024, B)
+        idx_q = (C.c_void_p * T)(*[h_idx[t].ctypes.data for t in range(T)])
+        lat = []
+        for i in range(220):
+            t0 = time.perf_counter()
+            eng.enqueue_host(den_ptr, idx_q, 0, len_ptrs, q, out_ptr)
+            eng.sync()
+            lat.append(time.perf_counter() - t0)
+        lat = np.array(lat[20:]) * 1e3
+        latency = {"query_size": q, "p50_ms": float(np.percentile(lat, 50)),
+                   "p95_ms": float(np.percentile(lat, 95)),
+                   "p99_ms": float(np.percentile(lat, 99)),
+                   "inferences_per_s_at_p99": q / (float(np.percentile(lat, 99)) * 1e-3)}
+
+    # ---------------- batch-size sweep (staged path), reference sweep shape 4^0..4^5 + larger
+    sweep = None
+    if not opts.no_sweep and rank == 0:
+        sweep = {}
+        for bs in [1, 4, 16, 64, 256, 1024, 4096, 16384, 65536]:
+            if bs > B:
+                continue
+            iters = 30
+            for i in range(3):
+                eng.enqueue_staged(i % nb, bs)
+            eng.sync()
+            eng.timer_start()
+            for i in range(iters):
+                eng.enqueue_staged(i % nb, bs)
+            ms = eng.timer_stop()
+            sweep[str(bs)] = {"ms_per_step": ms / iters, "inferences_per_s": bs * iters / (ms * 1e-3)}
+    barrier()
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if keep_host:
+        import torch
+        from oracle.torch_cpu_engine import TorchCpuModel, time_forward
+        n = min(int(opts.cpu_sample), B)
+        model = TorchCpuModel(spec, host_tables, fcs)
+        dense = lX[0][:n] if spec.m_den > 0 else None
+        ids = [lS_i[0][t][: n * spec.L] for t in range(spec.T)]
+        lens = [lS_l[0][t][:n] for t in range(spec.T)]
+        v, reps, secs, threads = time_forward(model, dense, ids, lens,
+                                              min_seconds=opts.cpu_seconds,
+                                              max_seconds=3 * opts.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d reps x first %d samples of staged batch 0 (%.1f s of CPU work)"
+                         % (reps, n, secs),
+               "what": "torch-CPU port of the reference CPU engine net (embedding_bag + addmm)",
+               "host_cores_available": len(os.sched_getaffinity(0))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": opts.steps, "warmup": max(3, opts.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if opts.precision == "fp32" else opts.precision,
+            "data": "synthetic",
+            "config": {"workload": "dlrm_%s (%s) %d tables x %s rows x D=%d, L=%d, "
+                                   "%d samples/step (=%d coalesced 1024-item queries), "
+                                   "staged in HBM" % (opts.config, spec.interaction_op, spec.T,
+                                                     spec.table_rows[0], spec.D, spec.L, B,
+                                                     max(1, B // 1024)),
+                       "global_batch": B * world, "parallelism": "replica x%d" % world,
+                       "l2_policy": "inputs larger than L2 (4.1 GB tables, uniform ids; "
+                                    "%d staged batches cycled)" % nb,
+                       "mlp_precision": opts.precision},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "latency_1024": latency, "sweep": sweep,
+            "hbm_bytes_allocated": eng.hbm_bytes(),
+        }
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    opts = parse_args()
+    if opts.impl == "reference":
+        return run_reference(opts)
+    return run_b200(opts)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

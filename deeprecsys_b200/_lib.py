@@ -1,0 +1,117 @@
+"""ctypes binding of include/drs_b200.h.
+
+There is deliberately no fallback: if libdrs_b200.so is missing the import of
+the library raises, and every call that returns a non-zero status raises
+DrsError with the library's message.
+"""
+from __future__ import absolute_import, division, print_function
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+# enums of drs_b200.h
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_COMM = range(6)
+MODEL_DLRM, MODEL_WND, MODEL_NCF, MODEL_DIN = range(4)
+INTERACT_CAT, INTERACT_DOT = 0, 1
+PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE = 0, 1, 2, 16
+STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS = range(6)
+SHARD_BLOB_BYTES = 192
+
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+MODEL_TYPES = {"dlrm": MODEL_DLRM, "wnd": MODEL_WND, "ncf": MODEL_NCF, "din": MODEL_DIN}
+
+
+class DrsError(RuntimeError):
+    def __init__(self, code, message):
+        super(DrsError, self).__init__("drs_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Spec(C.Structure):
+    _fields_ = [
+        ("model_type", C.c_int32), ("n_tables", C.c_int32),
+        ("table_rows", C.POINTER(C.c_int64)), ("emb_dim", C.c_int32),
+        ("n_bot", C.c_int32), ("ln_bot", C.POINTER(C.c_int32)),
+        ("n_top", C.c_int32), ("ln_top", C.POINTER(C.c_int32)),
+        ("interaction_op", C.c_int32), ("interaction_itself", C.c_int32),
+        ("max_batch", C.c_int32), ("max_lookups_per_table", C.c_int32),
+        ("precision", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("gpu_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float)]
+
+
+_PP = C.POINTER(C.c_void_p)
+_SIGNATURES = {
+    "drs_last_error": (C.c_char_p, []),
+    "drs_abi_version": (C.c_int, []),
+    "drs_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "drs_create": (C.c_int, [C.POINTER(Spec), C.c_int, _PP]),
+    "drs_destroy": (C.c_int, [C.c_void_p]),
+    "drs_out_dim": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "drs_load_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
+    "drs_load_fc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_int, C.c_int]),
+    "drs_stage_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _PP, C.c_int, _PP, C.c_int]),
+    "drs_infer_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.POINTER(Timing)]),
+    "drs_infer": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int, C.c_void_p,
+                            C.POINTER(Timing)]),
+    "drs_enqueue_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "drs_enqueue_host": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int,
+                                   C.c_void_p]),
+    "drs_sync": (C.c_int, [C.c_void_p]),
+    "drs_timer_start": (C.c_int, [C.c_void_p]),
+    "drs_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "drs_sparse_lengths_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64,
+                                         C.c_void_p, C.c_int, C.c_void_p]),
+    "drs_fetch_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "drs_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "drs_hbm_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "drs_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "drs_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "drs_host_alloc": (C.c_int, [_PP, C.c_int64]),
+    "drs_host_free": (C.c_int, [C.c_void_p]),
+    "drs_shard_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "drs_shard_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen libdrs_b200.so (built in-tree). Raises if it is not there."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                "libdrs_b200.so not found at %s: build it with "
+                "`python -m deeprecsys_b200.build` (no CPU fallback exists)" % path)
+        lib = C.CDLL(path)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if a symbol is missing
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise DrsError(code, load().drs_last_error().decode("utf-8", "replace"))
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)

@@ -1,0 +1,318 @@
+// sls_gather.cuh — K1: multi-table SparseLengthsSum gather-sum for sm_100a,
+// fused with the feature interaction's output layout (cat) or with the
+// pairwise-dot interaction itself (dot).
+//
+// Replaces, for all T tables of a query in ONE launch:
+//   SparseLengthsSum x T   /root/reference/models/dlrm_s_caffe2.py:319-325
+//   Concat(axis=1)         dlrm_s_caffe2.py:358-360            (cat)
+//   Concat(add_axis)+BatchMatMul+Flatten+BatchGather+Concat  :337-354  (dot)
+//
+// Numerics contract: Caffe2's CPU SparseLengthsSum accumulates
+// every output column in fp32, sequentially in index order, starting from 0.
+// Here one lane owns 4 adjacent columns of one (sample, table) segment and
+// walks that segment's rows in index order, so the pooled vectors are
+// bit-identical.  A segment is never split across lanes that would need a
+// cross-lane reduction.
+//
+// Mapping: a CTA owns a tile of SB consecutive samples x all T tables.
+// LPR = D/4 lanes cover one 4*LPR-float row with one 16-byte load each
+// (D=32: 8 lanes x 16 B = one 128-B line; a warp therefore has 4 segments in
+// flight).  Each lane group keeps UNROLL independent row loads outstanding and
+// applies the adds in order.  The tile's offsets and index spans are staged in
+// shared memory; index spans arrive by 1-D TMA bulk copies (cp.async.bulk ->
+// UBLKCP) completing on an mbarrier, one copy per table.
+#pragma once
+
+#include "common.cuh"
+
+namespace drs {
+
+constexpr int kSlsThreads = 256;
+constexpr int kSlsUnroll = 8;
+
+struct SlsTableDesc {
+  const float* rows;      // [n_rows, D] table in HBM
+  const int32_t* idx;     // ids of this table for the staged batch / query
+  const int32_t* off;     // [B+1] exclusive prefix of lengths
+  int64_t n_rows;
+  int32_t dst_col;        // first output column of this table's pooled vector
+  int32_t pad_;
+};
+
+struct SlsLaunch {
+  const SlsTableDesc* tables;
+  int T, B, D;
+  float* out;             // [B, ld_out]
+  int64_t ld_out;
+  int SB;                 // samples per CTA tile
+  int idx_cap;            // ints of smem per table index span (0 = read ids from global)
+  int vec_store;          // out/ld_out/dst_col all 16-B aligned
+  int* err_flag;          // SparseLengthsSum enforce violations
+  // dot interaction fusion (FUSE_DOT kernels only)
+  const float* dense;     // [B, ld_dense] bottom-MLP output (feature 0)
+  int64_t ld_dense;
+  int itself;             // arch_interaction_itself
+  float* pooled_tap;      // optional [B, T*D] copy of pooled vectors (debug tap), or nullptr
+};
+
+__host__ __device__ inline size_t sls_smem_bytes(int T, int SB, int idx_cap, int D, bool fuse_dot) {
+  size_t b = 16;                                        // mbarrier (+pad)
+  b += (size_t)T * idx_cap * sizeof(int32_t);           // index spans
+  b += (size_t)T * (SB + 1) * sizeof(int32_t);          // offsets
+  b = (b + 15) & ~size_t(15);
+  if (fuse_dot) b += (size_t)SB * (T + 1) * (D + 1) * sizeof(float);
+  return b;
+}
+
+// One segment: rows[ids[beg..end)] summed in order. Lane owns columns 4*lane..4*lane+3.
+template <bool SMEM_IDX>
+__device__ __forceinline__ float4 sls_segment_vec4(const float* __restrict__ rows_lane,
+                                                   uint32_t n_rows, int D,
+                                                   const int32_t* __restrict__ ids, int beg,
+                                                   int end, int* err_flag) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = beg;
+  for (; i + kSlsUnroll <= end; i += kSlsUnroll) {
+    int32_t id[kSlsUnroll];
+    float4 v[kSlsUnroll];
+#pragma unroll
+    for (int u = 0; u < kSlsUnroll; ++u) id[u] = SMEM_IDX ? ids[i + u] : __ldg(ids + i + u);
+#pragma unroll
+    for (int u = 0; u < kSlsUnroll; ++u) {
+      if ((uint32_t)id[u] < n_rows) {
+        v[u] = ldg_stream_f4(rows_lane + (int64_t)id[u] * D);
+      } else {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *err_flag = 1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSlsUnroll; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+  }
+  if (i < end) {  // tail: < UNROLL rows, still all loads first, adds in order
+    int32_t id[kSlsUnroll];
+    float4 v[kSlsUnroll];
+#pragma unroll
+    for (int u = 0; u < kSlsUnroll; ++u)
+      id[u] = (i + u < end) ? (SMEM_IDX ? ids[i + u] : __ldg(ids + i + u)) : -1;
+#pragma unroll
+    for (int u = 0; u < kSlsUnroll; ++u) {
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i + u < end) {
+        if ((uint32_t)id[u] < n_rows) v[u] = ldg_stream_f4(rows_lane + (int64_t)id[u] * D);
+        else *err_flag = 1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSlsUnroll; ++u)
+      if (i + u < end) {
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+  }
+  return acc;
+}
+
+// LPR: lanes per row (D == 4*LPR).  LPR == 0 selects the generic any-D path
+// (one warp per segment, lane <-> column, scalar loads).
+template <int LPR, bool FUSE_DOT>
+__global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  int32_t* sidx = reinterpret_cast<int32_t*>(smem_raw + 16);
+  int32_t* soff = sidx + (size_t)p.T * p.idx_cap;
+  float* spool = nullptr;  // [SB][T+1][D+1] (dot only)
+  if (FUSE_DOT) {
+    size_t o = 16 + ((size_t)p.T * p.idx_cap + (size_t)p.T * (p.SB + 1)) * sizeof(int32_t);
+    o = (o + 15) & ~size_t(15);
+    spool = reinterpret_cast<float*>(smem_raw + o);
+  }
+
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * p.SB;
+  const int sbe = min(p.SB, p.B - b0);
+  const int SB1 = p.SB + 1;
+  const bool use_smem_idx = p.idx_cap > 0;
+
+  // 1. offsets of the tile -> smem
+  for (int i = tid; i < p.T * SB1; i += kSlsThreads) {
+    const int t = i / SB1, j = i - t * SB1;
+    soff[i] = (j <= sbe) ? __ldg(p.tables[t].off + b0 + j) : 0;
+  }
+  if (use_smem_idx && tid == 0) {
+    mbar_init(bar, (uint32_t)p.T);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // 2. index spans of the tile -> smem by TMA bulk copies (one per table)
+  if (use_smem_idx) {
+    for (int t = tid; t < p.T; t += kSlsThreads) {
+      const int beg = soff[t * SB1], end = soff[t * SB1 + sbe];
+      const int a0 = beg & ~3;
+      const int n = (end - a0 + 3) & ~3;
+      if (n > 0 && n <= p.idx_cap) {
+        mbar_arrive_expect_tx(bar, (uint32_t)n * 4u);
+        tma_load_1d(sidx + (size_t)t * p.idx_cap, p.tables[t].idx + a0, (uint32_t)n * 4u, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+  }
+  if (FUSE_DOT) {  // feature 0 = bottom-MLP output
+    const int Dp = p.D + 1, F = p.T + 1;
+    for (int i = tid; i < sbe * p.D; i += kSlsThreads) {
+      const int lb = i / p.D, c = i - lb * p.D;
+      spool[(size_t)(lb * F) * Dp + c] = __ldg(p.dense + (int64_t)(b0 + lb) * p.ld_dense + c);
+    }
+  }
+  if (use_smem_idx) mbar_wait(bar, 0);
+
+  // 3. gather: lane groups walk segments
+  const int nseg = sbe * p.T;
+  if (LPR > 0) {
+    constexpr int L = LPR > 0 ? LPR : 1;
+    const int group = tid / L, lane = tid - group * L;
+    constexpr int ngroups = kSlsThreads / L;
+    for (int s = group; s < nseg; s += ngroups) {
+      const int t = s / sbe, lb = s - t * sbe;
+      const SlsTableDesc td = p.tables[t];
+      const int tile_beg = soff[t * SB1], tile_end = soff[t * SB1 + sbe];
+      const int beg = soff[t * SB1 + lb], end = soff[t * SB1 + lb + 1];
+      const int a0 = tile_beg & ~3;
+      const bool in_smem = use_smem_idx && (((tile_end - a0 + 3) & ~3) <= p.idx_cap);
+      const float* rows_lane = td.rows + lane * 4;
+      float4 acc;
+      if (in_smem)
+        acc = sls_segment_vec4<true>(rows_lane, (uint32_t)td.n_rows, p.D,
+                                     sidx + (size_t)t * p.idx_cap - a0, beg, end, p.err_flag);
+      else
+        acc = sls_segment_vec4<false>(rows_lane, (uint32_t)td.n_rows, p.D, td.idx, beg, end,
+                                      p.err_flag);
+      const int64_t b = b0 + lb;
+      if (FUSE_DOT) {
+        float* d = spool + (size_t)(lb * (p.T + 1) + 1 + t) * (p.D + 1) + lane * 4;
+        d[0] = acc.x; d[1] = acc.y; d[2] = acc.z; d[3] = acc.w;
+        if (p.pooled_tap)
+          *reinterpret_cast<float4*>(p.pooled_tap + b * ((int64_t)p.T * p.D) + (int64_t)t * p.D +
+                                     lane * 4) = acc;
+      } else {
+        float* o = p.out + b * p.ld_out + td.dst_col + lane * 4;
+        if (p.vec_store) {
+          *reinterpret_cast<float4*>(o) = acc;
+        } else {
+          o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+        }
+      }
+    }
+  } else {
+    // generic D: one warp per segment, lane <-> column (cols lane, lane+32, ...)
+    const int warp = tid / kWarp, lane = tid % kWarp;
+    constexpr int nwarps = kSlsThreads / kWarp;
+    for (int s = warp; s < nseg; s += nwarps) {
+      const int t = s / sbe, lb = s - t * sbe;
+      const SlsTableDesc td = p.tables[t];
+      const int beg = soff[t * SB1 + lb], end = soff[t * SB1 + lb + 1];
+      const int64_t b = b0 + lb;
+      for (int c = lane; c < p.D; c += kWarp) {
+        float acc = 0.f;
+        for (int i = beg; i < end; ++i) {
+          const int32_t id = __ldg(td.idx + i);
+          if ((uint32_t)id < (uint32_t)td.n_rows) acc += ldg_stream_f1(td.rows + (int64_t)id * p.D + c);
+          else *p.err_flag = 1;
+        }
+        if (FUSE_DOT) {
+          spool[(size_t)(lb * (p.T + 1) + 1 + t) * (p.D + 1) + c] = acc;
+          if (p.pooled_tap) p.pooled_tap[b * ((int64_t)p.T * p.D) + (int64_t)t * p.D + c] = acc;
+        } else {
+          p.out[b * p.ld_out + td.dst_col + c] = acc;
+        }
+      }
+    }
+  }
+
+  if (FUSE_DOT) {
+    // 4. pairwise dot: R[b] = [x, (T_i . T_j) for i in 0..F-1, j < i + itself]
+    __syncthreads();
+    const int F = p.T + 1, Dp = p.D + 1;
+    const int npair = p.itself ? F * (F + 1) / 2 : F * (F - 1) / 2;
+    for (int w = tid; w < sbe * npair; w += kSlsThreads) {
+      const int lb = w / npair, q = w - lb * npair;
+      // invert the row-major lower-triangle enumeration
+      int i, j;
+      if (p.itself) {
+        i = (int)((sqrtf(8.f * q + 1.f) - 1.f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= q) ++i;
+        while (i * (i + 1) / 2 > q) --i;
+        j = q - i * (i + 1) / 2;
+      } else {
+        i = (int)((sqrtf(8.f * q + 1.f) + 1.f) * 0.5f);
+        while (i * (i + 1) / 2 <= q) ++i;
+        while (i * (i - 1) / 2 > q) --i;
+        j = q - i * (i - 1) / 2;
+      }
+      const float* a = spool + (size_t)(lb * F + i) * Dp;
+      const float* c = spool + (size_t)(lb * F + j) * Dp;
+      float z = 0.f;
+      for (int k = 0; k < p.D; ++k) z = fmaf(a[k], c[k], z);
+      p.out[(int64_t)(b0 + lb) * p.ld_out + p.D + q] = z;
+    }
+    for (int w = tid; w < sbe * p.D; w += kSlsThreads) {
+      const int lb = w / p.D, c = w - lb * p.D;
+      p.out[(int64_t)(b0 + lb) * p.ld_out + c] = spool[(size_t)(lb * F) * Dp + c];
+    }
+  }
+}
+
+// lengths -> offsets (exclusive prefix sum), one CTA per table; also checks
+// Caffe2's enforce  sum(lengths) == len(indices)  when n_idx >= 0.
+// Integer-exact by construction.
+struct ScanTableDesc {
+  const int32_t* lengths;   // [B]
+  int32_t* off;             // [B+1]
+  int64_t n_idx;            // expected total, or -1
+};
+
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads) k_lengths_to_offsets(const ScanTableDesc* tabs,
+                                                                     int B, int* err_flag) {
+  __shared__ int32_t warp_sums[kScanThreads / kWarp];
+  __shared__ int32_t carry_s;
+  const ScanTableDesc td = tabs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
+  if (tid == 0) { carry_s = 0; td.off[0] = 0; }
+  __syncthreads();
+  for (int base = 0; base < B; base += kScanThreads) {
+    const int i = base + tid;
+    int32_t v = (i < B) ? td.lengths[i] : 0;
+    if (v < 0) { *err_flag = 1; v = 0; }
+    int32_t x = v;  // inclusive warp scan
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+      int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == kWarp - 1) warp_sums[warp] = x;
+    __syncthreads();
+    int32_t wprefix = 0;
+    for (int w = 0; w < warp; ++w) wprefix += warp_sums[w];
+    const int32_t carry = carry_s;
+    if (i < B) td.off[i + 1] = carry + wprefix + x;
+    __syncthreads();
+    if (tid == kScanThreads - 1) carry_s = carry + wprefix + x;
+    __syncthreads();
+  }
+  if (tid == 0 && td.n_idx >= 0 && (int64_t)carry_s != td.n_idx) *err_flag = 1;
+}
+
+// int64 ids -> int32 (the reference's Cast op, dlrm_s_caffe2.py:308)
+__global__ void k_cast_i64_i32(const int64_t* __restrict__ src, int32_t* __restrict__ dst,
+                               int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (int32_t)src[i];
+}
+
+}  // namespace drs

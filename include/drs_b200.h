@@ -1,0 +1,189 @@
+/*
+ * drs_b200.h — C-ABI of the B200 accelerator backend for DeepRecSys.
+ *
+ * This is the drop-in boundary for the per-query accelerator inference path.
+ * The reference has no native code; the interface it would bind is the python
+ * hand-off between the accel engine process and the model net:
+ *
+ *   accelInferenceEngine.py:46-83   per-packet serve loop (today: sleep)
+ *   inferenceEngine.py:200-215      request -> (dense, lengths, ids) slicing
+ *   models/dlrm_s_caffe2.py:162-174 DLRM_Wrapper.run_queues(ids, lengths, fc, B)
+ *   models/dlrm_s_caffe2.py:549-569 DLRM_Net.run(X, S_lengths, S_indices)
+ *   models/dlrm_s_caffe2.py:281-329 create_emb   -> SparseLengthsSum per table
+ *   models/dlrm_s_caffe2.py:223-279 create_mlp   -> FC + Relu/Sigmoid per layer
+ *   models/dlrm_s_caffe2.py:331-365 create_interactions (cat | dot)
+ *   models/{wide_and_deep,ncf,din}.py  sibling graphs
+ *
+ * Rules of the boundary: extern "C", plain pointers and sizes, caller-owned
+ * host buffers, engine-owned device memory, int status (0 = ok) plus a
+ * thread-local message from drs_last_error().  One submitting thread per
+ * engine handle.  There is no CPU fallback behind any entry point.
+ */
+#ifndef DRS_B200_H_
+#define DRS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRS_ABI_VERSION 1
+
+/* status codes */
+enum {
+  DRS_OK = 0,
+  DRS_ERR_INVALID = 1,     /* bad argument / spec (mirrors the reference's sys.exit checks) */
+  DRS_ERR_CUDA = 2,        /* CUDA runtime failure, message has the cudaError string */
+  DRS_ERR_STATE = 3,       /* weights/tables/batch not loaded yet */
+  DRS_ERR_INDEX = 4,       /* SparseLengthsSum enforce: idx out of range or sum(len) != len(idx) */
+  DRS_ERR_COMM = 5         /* peer-memory / multi-GPU exchange setup failure */
+};
+
+/* model graphs (reference: models/dlrm_s_caffe2.py, wide_and_deep.py, ncf.py, din.py) */
+enum { DRS_MODEL_DLRM = 0, DRS_MODEL_WND = 1, DRS_MODEL_NCF = 2, DRS_MODEL_DIN = 3 };
+
+/* arch_interaction_op (dlrm_s_caffe2.py:334-365) */
+enum { DRS_INTERACT_CAT = 0, DRS_INTERACT_DOT = 1 };
+
+/* MLP arithmetic: FP32 = FFMA parity path; TF32X3 = tcgen05 error-compensated
+ * (fp32-class accuracy); TF32 = tcgen05 single pass (throughput mode). */
+enum { DRS_PREC_FP32 = 0, DRS_PREC_TF32X3 = 1, DRS_PREC_TF32 = 2 };
+
+/* mlp ids for drs_load_fc */
+enum {
+  DRS_MLP_BOT = 0,         /* DLRM bottom MLP (dlrm_s_caffe2.py:376)                        */
+  DRS_MLP_TOP = 1,         /* DLRM/WnD/DIN top MLP; NCF: the MLP tower ln_top[:-1] (ncf.py:332) */
+  DRS_MLP_FINAL = 2,       /* NCF final FC over [Zmf, tower] (ncf.py:339-343)               */
+  DRS_MLP_ATTN_BASE = 16   /* DIN attention unit i -> DRS_MLP_ATTN_BASE + i (din.py:260-278) */
+};
+
+/* stage taps for drs_fetch_stage (stage-level parity) */
+enum {
+  DRS_STAGE_POOLED = 0,    /* [B, T*D] pooled vectors, table-major columns   */
+  DRS_STAGE_BOT = 1,       /* layer k output of the bottom MLP [B, ln_bot[k+1]] (DIN: summed attention output, layer ignored) */
+  DRS_STAGE_INTERACT = 2,  /* top-MLP input [B, ln_top[0]]                   */
+  DRS_STAGE_TOP = 3,       /* layer k output of the top MLP                  */
+  DRS_STAGE_OUT = 4,       /* final output [B, out_dim]                      */
+  DRS_STAGE_OFFSETS = 5    /* int32 offsets [T, B+1] reinterpret as float bits (bit-exact bucketing check) */
+};
+
+typedef struct drs_engine drs_engine;
+
+/* Integers of the model spec (utils/utils.py:22-37 flags after the per-model
+ * adjustments of dlrm_s_caffe2.py:404-440, wide_and_deep.py:332-350,
+ * ncf.py:373-388, din.py:346-359). */
+typedef struct {
+  int32_t model_type;            /* DRS_MODEL_*                                              */
+  int32_t n_tables;              /* T                                                        */
+  const int64_t* table_rows;     /* [T] rows per table                                       */
+  int32_t emb_dim;               /* D = arch_sparse_feature_size                             */
+  int32_t n_bot;                 /* number of widths in ln_bot (layers + 1); 0 if none       */
+  const int32_t* ln_bot;         /* DLRM: bottom widths; WnD: [m_den]; DIN: attention [3D,..,D] */
+  int32_t n_top;                 /* number of widths in ln_top                               */
+  const int32_t* ln_top;         /* adjusted: ln_top[0] = interaction width                  */
+  int32_t interaction_op;        /* DRS_INTERACT_*  (DLRM only)                              */
+  int32_t interaction_itself;    /* arch_interaction_itself                                  */
+  int32_t max_batch;             /* largest query (samples)                                  */
+  int32_t max_lookups_per_table; /* largest sum(lengths) of one table in one query           */
+  int32_t precision;             /* DRS_PREC_*                                               */
+  int32_t reserved;
+} drs_spec;
+
+/* per-call timing, milliseconds */
+typedef struct {
+  float h2d_ms;      /* host->device input copies (0 for staged batches) */
+  float gpu_ms;      /* kernels, CUDA-event time on the engine stream    */
+  float d2h_ms;      /* result read-back                                  */
+  float total_ms;    /* wall clock of the call                            */
+} drs_timing;
+
+const char* drs_last_error(void);
+int drs_abi_version(void);
+int drs_device_count(int* n_out);
+
+/* lifecycle */
+int drs_create(const drs_spec* spec, int device, drs_engine** out);
+int drs_destroy(drs_engine* e);
+int drs_out_dim(const drs_engine* e, int* out_dim);
+
+/* parameters: host -> HBM.  W is [out_dim, in_dim] row-major exactly as the
+ * Caffe2 FC blob (dlrm_s_caffe2.py:247), b is [out_dim]. */
+int drs_load_table(drs_engine* e, int table, const float* rows, int64_t n_rows, int dim);
+int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const float* b,
+                int out_dim, int in_dim);
+
+/* Pre-stage one generated batch in HBM (the reference pre-generates all
+ * batches at engine start: inferenceEngine.py:80-88).  idx[t] has
+ * sum(lengths[t][0..n_samples)) entries, int64 (as np.array(list) yields) or
+ * int32 (after the reference's Cast, dlrm_s_caffe2.py:308).  dense may be NULL
+ * for models without dense input (NCF, DIN). */
+int drs_stage_batch(drs_engine* e, int batch_id, const float* dense,
+                    const void* const* idx, int idx_is_i64,
+                    const int32_t* const* lengths, int n_samples);
+
+/* Serve "first batch_size samples of staged batch batch_id"
+ * (inferenceEngine.py:200-215).  out may be NULL (result stays in HBM). */
+int drs_infer_staged(drs_engine* e, int batch_id, int batch_size, float* out, drs_timing* t);
+
+/* Serve a query from HOST buffers: H2D of dense/ids/lengths, lengths->offsets
+ * on the GPU, gather, interaction, MLPs, D2H of [batch_size, out_dim]. */
+int drs_infer(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
+              const int32_t* const* lengths, int batch_size, float* out, drs_timing* t);
+
+/* Asynchronous halves used by the serving loop and the bench harness:
+ * enqueue does not synchronise; drs_sync waits for the stream and reports the
+ * SparseLengthsSum enforce flag. */
+int drs_enqueue_staged(drs_engine* e, int batch_id, int batch_size);
+int drs_enqueue_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
+                     const int32_t* const* lengths, int batch_size, float* out_pinned);
+int drs_sync(drs_engine* e);
+
+/* CUDA-event stopwatch on the engine's stream (the stream the kernels run on). */
+int drs_timer_start(drs_engine* e);
+int drs_timer_stop(drs_engine* e, float* elapsed_ms);
+
+/* Operator entry: SparseLengthsSum(table, idx, lengths) -> out[n_segments, D]
+ * on loaded table `table` with host idx/lengths (Caffe2 op semantics used at
+ * dlrm_s_caffe2.py:319-325). */
+int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is_i64,
+                           int64_t n_idx, const int32_t* lengths, int n_segments, float* out);
+
+/* Debug taps of the last served query (device -> host). */
+int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t capacity_floats,
+                    int* rows, int* cols);
+
+/* Bookkeeping the bench reports. */
+int drs_launch_count(const drs_engine* e, int64_t* n_kernel_launches);
+int drs_hbm_bytes(const drs_engine* e, int64_t* bytes_allocated);
+
+/* Per-segment CUDA-event profiling of the served graph, on the engine stream:
+ * between begin and end every query records 4 events (start | before K1 |
+ * after K1 | end); end returns the summed times of the pre-gather kernels
+ * (bottom MLP / copies), the K1 gather(+interaction) kernel, and the
+ * post-gather kernels (top MLP ...) over n_steps queries. */
+int drs_profile_begin(drs_engine* e, int max_steps);
+int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms, float* post_ms);
+
+/* Pinned host memory for the upload path (so H2D/D2H are true async DMA). */
+int drs_host_alloc(void** ptr, int64_t bytes);
+int drs_host_free(void* ptr);
+
+/* Multi-GPU, one process per GPU (table-wise sharding).
+ * Each rank owns tables {t : t % world == rank}; after the gather every rank
+ * holds all T pooled vectors for its slice of the query's samples.  The
+ * exchange is done by the gather kernel itself storing pooled rows straight
+ * into the destination rank's slab through peer-mapped memory (CUDA IPC over
+ * NVLink), followed by a flag barrier — no pack/unpack kernels.
+ *   1. every rank: drs_shard_export(e, handle_out)   (64-byte IPC handle + metadata)
+ *   2. ranks all-gather the blobs (torch.distributed / any transport)
+ *   3. every rank: drs_shard_connect(e, rank, world, all_blobs)
+ */
+#define DRS_SHARD_BLOB_BYTES 192
+int drs_shard_export(drs_engine* e, void* blob_out);
+int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DRS_B200_H_ */

@@ -1,0 +1,81 @@
+"""Shared builders for the parity tests: a small seeded case per model graph,
+generated exactly the way an engine process does it (seed -> datagen inputs ->
+datagen targets -> parameters)."""
+import os
+
+import numpy as np
+
+from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator, slice_request
+from deeprecsys_b200.spec import ModelSpec, draw_all_parameters
+from deeprecsys_b200.utils.utils import cli
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIG_DIR = os.path.join(ROOT, "deeprecsys_b200", "models", "configs")
+
+SMALL = {
+    # name -> argv  (small tables so the oracle finishes in seconds)
+    "dlrm_cat": ["--arch_embedding_size", "5000-6000-7000-8000-5000-6000-7000-8000",
+                 "--arch_sparse_feature_size", "32", "--arch_mlp_bot", "128-64-32",
+                 "--arch_mlp_top", "256-64-1", "--arch_interaction_op", "cat",
+                 "--num_indices_per_lookup", "80"],
+    "dlrm_dot": ["--arch_embedding_size", "5000-6000-7000-8000-5000-6000-7000-8000",
+                 "--arch_sparse_feature_size", "32", "--arch_mlp_bot", "128-64-32",
+                 "--arch_mlp_top", "256-64-1", "--arch_interaction_op", "dot",
+                 "--num_indices_per_lookup", "80"],
+    "dlrm_dot_itself": ["--arch_embedding_size", "500-600-700", "--arch_sparse_feature_size", "16",
+                        "--arch_mlp_bot", "13-16", "--arch_mlp_top", "32-1",
+                        "--arch_interaction_op", "dot", "--arch_interaction_itself",
+                        "--num_indices_per_lookup", "5"],
+    "dlrm_rm2_like": ["--arch_embedding_size", "-".join(["3000"] * 32),
+                      "--arch_sparse_feature_size", "64", "--arch_mlp_bot", "256-128-64",
+                      "--arch_mlp_top", "128-64-1", "--arch_interaction_op", "cat",
+                      "--num_indices_per_lookup", "120"],
+    "dlrm_rm3_like": ["--arch_embedding_size", "-".join(["4000"] * 10),
+                      "--arch_sparse_feature_size", "32", "--arch_mlp_bot", "2560-1024-256-32",
+                      "--arch_mlp_top", "512-256-1", "--arch_interaction_op", "cat",
+                      "--num_indices_per_lookup", "20"],
+    "dlrm_odd": ["--arch_embedding_size", "50-60-70", "--arch_sparse_feature_size", "6",
+                 "--arch_mlp_bot", "7-9-6", "--arch_mlp_top", "11-5-1",
+                 "--arch_interaction_op", "dot", "--num_indices_per_lookup", "3"],
+    "wnd": ["--model_type", "wnd", "--arch_embedding_size", "-".join(["2000"] * 27),
+            "--arch_sparse_feature_size", "32", "--arch_mlp_bot", "512",
+            "--arch_mlp_top", "1024-512-256-1", "--arch_interaction_op", "cat",
+            "--num_indices_per_lookup", "1"],
+    "ncf": ["--model_type", "ncf", "--arch_embedding_size", "1400-1400-280-280",
+            "--arch_sparse_feature_size", "64", "--arch_mlp_bot", "512",
+            "--arch_mlp_top", "256-256-128-64-64", "--arch_interaction_op", "cat",
+            "--num_indices_per_lookup", "1"],
+    "din": ["--model_type", "din", "--arch_embedding_size", "1000-100-2000-2000",
+            "--user_behavior_tables", "0", "--arch_sparse_feature_size", "32",
+            "--arch_mlp_bot", "1", "--arch_mlp_top", "200-80-2", "--arch_interaction_op", "cat",
+            "--num_indices_per_lookup", "3"],
+    "din_many": ["--model_type", "din", "--arch_embedding_size", "1000-100-2000-2000",
+                 "--user_behavior_tables", "10", "--arch_sparse_feature_size", "32",
+                 "--arch_mlp_bot", "8-4", "--arch_mlp_top", "200-80-2",
+                 "--arch_interaction_op", "cat", "--num_indices_per_lookup", "3"],
+}
+
+
+class Case(object):
+    pass
+
+
+def make_case(name, num_batches=2, max_batch=64, seed=123):
+    argv = list(SMALL[name]) + ["--num_batches", str(num_batches),
+                                "--max_mini_batch_size", str(max_batch),
+                                "--numpy_rand_seed", str(seed)]
+    c = Case()
+    c.name = name
+    c.args = cli(argv)                                   # seeds numpy
+    gen = DLRMDataGenerator(c.args)
+    _, c.lX, c.lS_l, c.lS_i = gen.generate_input_data()
+    _, c.lT = gen.generate_output_data()
+    c.spec = ModelSpec(c.args)
+    c.tables, c.fcs = draw_all_parameters(c.spec)
+    return c
+
+
+def request(c, batch_id, batch_size):
+    d, l, i = slice_request(c.lX, c.lS_l, c.lS_i, batch_id, batch_size, c.spec.L)
+    dense = d if c.spec.m_den > 0 else None
+    return dense, [np.ascontiguousarray(x) for x in i], [np.ascontiguousarray(x) for x in l]

@@ -1,0 +1,162 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the
+same seeded inputs.  Tolerances:
+  index/offset bucketing ............ bit-exact (int32)
+  pooled vectors (SparseLengthsSum) . bit-exact (fp32, sequential order)
+  cat interaction ................... bit-exact
+  dot interaction ................... rtol 1e-5 / atol 1e-6
+  FC stack, fp32 FFMA path .......... atol 1e-5 on outputs (rtol 1e-4 on hidden layers)
+"""
+import numpy as np
+import pytest
+
+from deeprecsys_b200 import _lib
+from deeprecsys_b200.engine import AccelEngine
+from oracle import numpy_oracle as O
+from tests.helpers import SMALL, make_case, request
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(c, precision="fp32"):
+    eng = AccelEngine(args=c.args, max_batch=c.args.max_mini_batch_size, precision=precision)
+    eng.load_parameters(c.tables, c.fcs)
+    return eng
+
+
+def _check_stages(c, eng, st, B, fc_atol=1e-5, fc_rtol=1e-4):
+    spec = c.spec
+    pooled = eng.fetch_stage(_lib.STAGE_POOLED)
+    assert pooled.shape == st["pooled"].shape
+    assert np.array_equal(pooled.view(np.uint32), st["pooled"].view(np.uint32)), "pooled not bit-exact"
+    off = eng.fetch_stage(_lib.STAGE_OFFSETS)
+    assert off.dtype == np.int32 and off.shape == (spec.T, B + 1)
+    inter = eng.fetch_stage(_lib.STAGE_INTERACT)
+    assert inter.shape == st["interact"].shape
+    if spec.model_type in ("dlrm",) and spec.interaction_op == "cat":
+        # embedding columns are copies of pooled: exact; dense block is FC output
+        D = spec.D
+        assert np.array_equal(inter[:, D:], st["interact"][:, D:])
+        np.testing.assert_allclose(inter[:, :D], st["interact"][:, :D], rtol=fc_rtol, atol=fc_atol)
+    elif spec.model_type == "wnd":
+        assert np.array_equal(inter, st["interact"]), "wnd cat must be exact"
+    else:
+        np.testing.assert_allclose(inter, st["interact"], rtol=fc_rtol, atol=fc_atol)
+    if spec.model_type == "dlrm":
+        for k, ref in enumerate(st["bot"]):
+            np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_BOT, k), ref, rtol=fc_rtol,
+                                       atol=fc_atol)
+    for k, ref in enumerate(st["top"]):
+        np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_TOP, k), ref, rtol=fc_rtol,
+                                   atol=fc_atol)
+    out = eng.fetch_stage(_lib.STAGE_OUT)
+    np.testing.assert_allclose(out, st["out"], rtol=fc_rtol, atol=fc_atol)
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_model_stage_parity_host_path(name):
+    mb = 16 if name == "dlrm_rm3_like" else 48
+    c = make_case(name, num_batches=2, max_batch=mb)
+    with _engine(c) as eng:
+        for batch_id, B in [(0, mb), (1, 5), (0, 1)]:
+            dense, ids, lengths = request(c, batch_id, B)
+            st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+            out, tm = eng.infer(dense, ids, lengths, B)
+            assert out.shape == (B, c.spec.out_dim)
+            np.testing.assert_allclose(out, st["out"], rtol=1e-4, atol=1e-5)
+            _check_stages(c, eng, st, B)
+            assert tm.gpu_ms > 0
+        assert eng.launch_count() > 0
+
+
+@pytest.mark.parametrize("name", ["dlrm_cat", "dlrm_dot", "wnd", "ncf", "din_many"])
+def test_staged_path_matches_host_path_bitwise(name):
+    c = make_case(name, num_batches=2, max_batch=40)
+    with _engine(c) as eng:
+        for j in range(2):
+            dense, ids, lengths = request(c, j, 40)
+            eng.stage_batch(j, dense, [i.astype(np.int64) for i in ids], lengths)   # int64 as np.array(list)
+        for batch_id, B in [(1, 40), (0, 17), (1, 1)]:
+            dense, ids, lengths = request(c, batch_id, B)
+            out_h, _ = eng.infer(dense, ids, lengths, B)
+            out_s, tm = eng.infer_staged(batch_id, B)
+            assert np.array_equal(out_h, out_s)
+            assert tm.h2d_ms == 0.0
+            st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+            _check_stages(c, eng, st, B)
+
+
+@pytest.mark.parametrize("D", [2, 4, 6, 8, 16, 32, 64, 128, 12, 200])
+def test_sls_operator_bitexact_ragged(D):
+    rng = np.random.RandomState(D)
+    rows = 3001
+    W = rng.uniform(-1, 1, size=(rows, D)).astype(np.float32)
+    # ragged segments incl. empty ones and a long one
+    lengths = rng.randint(0, 40, size=97).astype(np.int32)
+    lengths[3] = 0
+    lengths[50] = 333
+    idx = rng.randint(0, rows, size=int(lengths.sum())).astype(np.int64)
+    argv = ["--arch_embedding_size", str(rows), "--arch_sparse_feature_size", str(D),
+            "--arch_mlp_bot", "4-%d" % D, "--arch_mlp_top", "4-1", "--arch_interaction_op", "cat"]
+    from deeprecsys_b200.utils.utils import cli
+    with AccelEngine(args=cli(argv), max_batch=8) as eng:
+        eng.load_table(0, W)
+        ref = O.sparse_lengths_sum(W, idx, lengths)
+        got = eng.sparse_lengths_sum(0, idx, lengths)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        got32 = eng.sparse_lengths_sum(0, idx.astype(np.int32), lengths)
+        assert np.array_equal(got32.view(np.uint32), ref.view(np.uint32))
+        # all-empty and single-segment edge cases
+        z = eng.sparse_lengths_sum(0, np.zeros(0, np.int64), np.zeros(5, np.int32))
+        assert np.array_equal(z, np.zeros((5, D), np.float32))
+        one = eng.sparse_lengths_sum(0, np.array([7], np.int64), np.array([1], np.int32))
+        assert np.array_equal(one, W[7:8])
+
+
+def test_sls_enforce_errors():
+    from deeprecsys_b200.utils.utils import cli
+    argv = ["--arch_embedding_size", "100", "--arch_sparse_feature_size", "32",
+            "--arch_mlp_bot", "4-32", "--arch_mlp_top", "4-1", "--arch_interaction_op", "cat"]
+    W = np.ones((100, 32), np.float32)
+    with AccelEngine(args=cli(argv), max_batch=8) as eng:
+        eng.load_table(0, W)
+        with pytest.raises(_lib.DrsError) as ei:          # index out of range
+            eng.sparse_lengths_sum(0, np.array([1, 100], np.int64), np.array([2], np.int32))
+        assert ei.value.code == _lib.ERR_INDEX
+        with pytest.raises(_lib.DrsError) as ei:          # sum(lengths) != len(indices)
+            eng.sparse_lengths_sum(0, np.array([1, 2, 3], np.int64), np.array([2], np.int32))
+        assert ei.value.code == _lib.ERR_INDEX
+        # engine still usable afterwards
+        ok = eng.sparse_lengths_sum(0, np.array([1, 2], np.int64), np.array([2], np.int32))
+        assert np.array_equal(ok, 2 * np.ones((1, 32), np.float32))
+        with pytest.raises(_lib.DrsError) as ei:          # weights not loaded yet
+            eng.infer(np.zeros((1, 4), np.float32), [np.array([0], np.int32)],
+                      [np.array([1], np.int32)], 1)
+        assert ei.value.code == _lib.ERR_STATE
+
+
+def test_offsets_bitexact_variable_lengths():
+    """lengths -> offsets on the GPU vs numpy cumsum, ragged lengths, B > one scan chunk."""
+    from deeprecsys_b200.utils.utils import cli
+    rng = np.random.RandomState(7)
+    T, D, B = 3, 32, 1000
+    argv = ["--arch_embedding_size", "-".join(["500"] * T), "--arch_sparse_feature_size", str(D),
+            "--arch_mlp_bot", "8-32", "--arch_mlp_top", "16-1", "--arch_interaction_op", "cat",
+            "--num_indices_per_lookup", "12"]
+    args = cli(argv)
+    spec_tables = [rng.uniform(-1, 1, (500, D)).astype(np.float32) for _ in range(T)]
+    from deeprecsys_b200.spec import ModelSpec, draw_all_parameters
+    spec = ModelSpec(args)
+    _, fcs = draw_all_parameters(spec)
+    lengths = [rng.randint(0, 13, size=B).astype(np.int32) for _ in range(T)]
+    ids = [rng.randint(0, 500, size=int(l.sum())).astype(np.int32) for l in lengths]
+    dense = rng.rand(B, 8).astype(np.float32)
+    with AccelEngine(args=args, max_batch=B) as eng:
+        eng.load_parameters(spec_tables, fcs)
+        out, _ = eng.infer(dense, ids, lengths, B)
+        off = eng.fetch_stage(_lib.STAGE_OFFSETS)
+        for t in range(T):
+            assert np.array_equal(off[t], O.lengths_to_offsets(lengths[t]))
+        st = O.forward(spec, spec_tables, fcs, dense, ids, lengths)
+        pooled = eng.fetch_stage(_lib.STAGE_POOLED)
+        assert np.array_equal(pooled.view(np.uint32), st["pooled"].view(np.uint32))
+        np.testing.assert_allclose(out, st["out"], rtol=1e-4, atol=1e-5)
