@@ -66,7 +66,7 @@ namespace {
 struct Layer {
   float* W = nullptr;   // [n_units, out, in]
   float* b = nullptr;   // [n_units, out]
-  float* W_lo = nullptr;  // tf32x3: low part of the split weights (same shape)
+  float* Wsplit = nullptr;  // tensor-core path: [n_units][2][out][in] = (top-19-bit part, remainder)
   int out = 0, in = 0;
   int n_units = 1;
   int act = kActRelu;
@@ -169,8 +169,8 @@ int alloc_mlp_buffers(drs_engine* e, Mlp& m, const std::vector<int32_t>& ln, int
     l.loaded.assign(n_units, 0);
     TRY(dev_alloc_t(e, &l.W, (size_t)n_units * l.out * l.in));
     TRY(dev_alloc_t(e, &l.b, (size_t)n_units * l.out));
-    if (e->spec.precision == DRS_PREC_TF32X3)
-      TRY(dev_alloc_t(e, &l.W_lo, (size_t)n_units * l.out * l.in));
+    if (e->spec.precision != DRS_PREC_FP32)
+      TRY(dev_alloc_t(e, &l.Wsplit, (size_t)n_units * 2 * l.out * l.in));
     TRY(dev_alloc_t(e, &l.y, (size_t)n_units * e->spec.max_batch * l.out));
   }
   return DRS_OK;
@@ -238,12 +238,14 @@ int write_descs(drs_engine* e, InputSet& s, const std::vector<int64_t>& n_idx) {
 
 // ------------------------------------------------------------ launchers
 int launch_fc(drs_engine* e, const Layer& l, const float* X, int64_t ldx, int64_t x_bstride,
-              float* Y, int64_t ldy, int64_t y_bstride, int M) {
+              int64_t x_rows_total, float* Y, int64_t ldy, int64_t y_bstride, int M) {
   if (M <= 0) return DRS_OK;
-  if (e->spec.precision != DRS_PREC_FP32 && tc_fc_supported(l.out, l.in, ldx, ldy, X, Y)) {
+  if (e->spec.precision != DRS_PREC_FP32 && l.Wsplit && tc_fc_supported(l.out, l.in, ldx, X) &&
+      (l.n_units == 1 || x_bstride % ldx == 0)) {
     TcFcLaunch q{};
-    q.X = X; q.ldx = ldx; q.x_bstride = x_bstride;
-    q.W = l.W; q.W_lo = l.W_lo; q.w_bstride = (int64_t)l.out * l.in;
+    q.X = X; q.ldx = ldx; q.x_rows = x_rows_total;
+    q.x_rows_per_unit = l.n_units > 1 ? x_bstride / ldx : 0;
+    q.Wsplit = l.Wsplit;
     q.bias = l.b; q.b_bstride = l.out;
     q.Y = Y; q.ldy = ldy; q.y_bstride = y_bstride;
     q.M = M; q.N = l.out; q.K = l.in; q.act = l.act;
@@ -271,18 +273,18 @@ int launch_fc(drs_engine* e, const Layer& l, const float* X, int64_t ldx, int64_
 }
 
 // chain an MLP; the last layer may be redirected into a column block of a wider buffer
-int run_mlp(drs_engine* e, Mlp& m, const float* X, int64_t ldx, int64_t x_bstride, int M,
+int run_mlp(drs_engine* e, Mlp& m, const float* X, int64_t ldx, int64_t x_rows_total, int M,
             float* last_y = nullptr, int64_t last_ldy = 0) {
   const int nl = (int)m.layers.size();
   const float* in = X;
-  int64_t ld_in = ldx, bs_in = x_bstride;
+  int64_t ld_in = ldx, bs_in = 0, rows_in = x_rows_total;
   for (int i = 0; i < nl; ++i) {
     Layer& l = m.layers[i];
     float* y = l.y;
     int64_t ldy = l.out, bsy = (int64_t)e->spec.max_batch * l.out;
     if (i == nl - 1 && last_y) { y = last_y; ldy = last_ldy; bsy = 0; }
-    TRY(launch_fc(e, l, in, ld_in, bs_in, y, ldy, bsy, M));
-    in = y; ld_in = ldy; bs_in = bsy;
+    TRY(launch_fc(e, l, in, ld_in, bs_in, rows_in, y, ldy, bsy, M));
+    in = y; ld_in = ldy; bs_in = bsy; rows_in = e->spec.max_batch;
   }
   return DRS_OK;
 }
@@ -390,17 +392,17 @@ int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
     case DRS_MODEL_DLRM: {
       const bool dot = e->spec.interaction_op == DRS_INTERACT_DOT;
       if (dot) {
-        TRY(run_mlp(e, e->bot, s.dense, e->m_den, 0, B, e->dense_out, D));
+        TRY(run_mlp(e, e->bot, s.dense, e->m_den, s.n, B, e->dense_out, D));
         PROF_MARK(1);
         TRY(launch_gather(e, s, B, e->R, e->ld_R, true, e->P));
         PROF_MARK(2);
       } else {
-        TRY(run_mlp(e, e->bot, s.dense, e->m_den, 0, B, e->R, e->ld_R));
+        TRY(run_mlp(e, e->bot, s.dense, e->m_den, s.n, B, e->R, e->ld_R));
         PROF_MARK(1);
         TRY(launch_gather(e, s, B, e->R, e->ld_R, false, nullptr));
         PROF_MARK(2);
       }
-      TRY(run_mlp(e, e->top, e->R, e->ld_R, 0, B));
+      TRY(run_mlp(e, e->top, e->R, e->ld_R, e->spec.max_batch, B));
       break;
     }
     case DRS_MODEL_WND: {
@@ -411,7 +413,7 @@ int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, s, B, e->R, e->ld_R, false, nullptr));
       PROF_MARK(2);
-      TRY(run_mlp(e, e->top, e->R, e->ld_R, 0, B));
+      TRY(run_mlp(e, e->top, e->R, e->ld_R, e->spec.max_batch, B));
       break;
     }
     case DRS_MODEL_NCF: {
@@ -424,8 +426,8 @@ int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
                                                                  D);
       CU(cudaGetLastError());
       e->launches += 1;
-      TRY(run_mlp(e, e->top, e->P + 2 * D, ldp, 0, B, e->F + D, ldf));
-      TRY(run_mlp(e, e->fin, e->F, ldf, 0, B));
+      TRY(run_mlp(e, e->top, e->P + 2 * D, ldp, e->spec.max_batch, B, e->F + D, ldf));
+      TRY(run_mlp(e, e->fin, e->F, ldf, e->spec.max_batch, B));
       break;
     }
     case DRS_MODEL_DIN: {
@@ -434,19 +436,20 @@ int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, s, B, e->P, ldp, false, nullptr));
       PROF_MARK(2);
-      k_din_concat<<<ew_grid((int64_t)nu * B * D), 256, 0, e->stream>>>(e->P, ldp, e->C, B, D, nu,
-                                                                        T - 2);
+      k_din_concat<<<ew_grid((int64_t)nu * B * D), 256, 0, e->stream>>>(
+          e->P, ldp, e->C, (int64_t)e->spec.max_batch * 3 * D, B, D, nu, T - 2);
       CU(cudaGetLastError());
       e->launches += 1;
       // attention MLPs, batched over units (each unit has its own weights)
       {
         const int nl = (int)e->bot.layers.size();
         const float* in = e->C;
-        int64_t ld_in = 3 * D, bs_in = (int64_t)B * 3 * D;
+        int64_t ld_in = 3 * D, bs_in = (int64_t)e->spec.max_batch * 3 * D;
         for (int i = 0; i < nl; ++i) {
           Layer& l = e->bot.layers[i];
           const int64_t bsy = (int64_t)e->spec.max_batch * l.out;
-          TRY(launch_fc(e, l, in, ld_in, bs_in, l.y, l.out, bsy, B));
+          TRY(launch_fc(e, l, in, ld_in, bs_in, (int64_t)nu * e->spec.max_batch, l.y, l.out, bsy,
+                        B));
           in = l.y; ld_in = l.out; bs_in = bsy;
         }
       }
@@ -465,7 +468,7 @@ int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
         CU(cudaGetLastError());
         e->launches += 1;
       }
-      TRY(run_mlp(e, e->top, e->R, e->ld_R, 0, B));
+      TRY(run_mlp(e, e->top, e->R, e->ld_R, e->spec.max_batch, B));
       break;
     }
     default:
@@ -722,7 +725,7 @@ int drs_destroy(drs_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (float* t : e->tables) cudaFree(t);
   for (Mlp* m : {&e->bot, &e->top, &e->fin})
-    for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.W_lo); cudaFree(l.y); }
+    for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wsplit); cudaFree(l.y); }
   cudaFree(e->R); cudaFree(e->P); cudaFree(e->dense_out); cudaFree(e->F); cudaFree(e->C);
   for (auto& kv : e->staged) free_input_set(kv.second);
   free_input_set(e->slot);
@@ -788,8 +791,8 @@ int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const floa
                      e->stream));
   CU(cudaMemcpyAsync(l.b + (size_t)unit * l.out, b, (size_t)l.out * sizeof(float),
                      cudaMemcpyHostToDevice, e->stream));
-  if (l.W_lo) {
-    int rc = tc_split_weights(l.W + unit * wcount, l.W_lo + unit * wcount, (int64_t)wcount,
+  if (l.Wsplit) {
+    int rc = tc_split_weights(l.W + unit * wcount, l.Wsplit + unit * 2 * wcount, (int64_t)wcount,
                               e->stream);
     if (rc != 0) return fail(DRS_ERR_CUDA, "weight split failed: %s",
                              cudaGetErrorString((cudaError_t)rc));

@@ -33,9 +33,10 @@ __global__ void k_add_cols(const float* __restrict__ a, const float* __restrict_
   }
 }
 
-// pooled: [B, T*D]; cat: [n_units, B, 3D]; unit i uses behaviour table 1 + i, ad table = ad_t.
+// pooled: [B, T*D]; cat: n_units blocks of [B, 3D], unit_stride floats apart; unit i uses
+// behaviour table 1 + i, ad table = ad_t.
 __global__ void k_din_concat(const float* __restrict__ pooled, int64_t ldp, float* __restrict__ cat,
-                             int B, int D, int n_units, int ad_t) {
+                             int64_t unit_stride, int B, int D, int n_units, int ad_t) {
   const int64_t n = (int64_t)n_units * B * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -44,7 +45,7 @@ __global__ void k_din_concat(const float* __restrict__ pooled, int64_t ldp, floa
     const int64_t b = r / D, c = r - b * D;
     const float eu = pooled[b * ldp + (1 + u) * D + c];
     const float ea = pooled[b * ldp + (int64_t)ad_t * D + c];
-    float* o = cat + (u * B + b) * (3 * (int64_t)D);
+    float* o = cat + u * unit_stride + b * (3 * (int64_t)D);
     o[c] = eu;
     o[D + c] = ea;
     o[2 * D + c] = eu + ea;

@@ -160,3 +160,37 @@ def test_offsets_bitexact_variable_lengths():
         pooled = eng.fetch_stage(_lib.STAGE_POOLED)
         assert np.array_equal(pooled.view(np.uint32), st["pooled"].view(np.uint32))
         np.testing.assert_allclose(out, st["out"], rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- tensor-core MLP path
+@pytest.mark.parametrize("name", ["dlrm_cat", "dlrm_dot", "dlrm_rm2_like", "dlrm_rm3_like", "wnd",
+                                  "ncf", "din", "din_many", "dlrm_odd"])
+def test_tf32x3_tensor_core_path_fp32_class_accuracy(name):
+    """tcgen05 kind::tf32 with hi/lo split operands (3 MMAs per product).  Final
+    outputs: same tolerance as the fp32 FFMA path (atol 1e-5).  Hidden layers:
+    atol 5e-5 / rtol 2e-4 — the tensor core accumulates in fp32 with
+    round-toward-zero, which leaves a bias of ~K/8*3 half-ulps (2e-5 at K=2560),
+    still ~50x tighter than single-pass TF32."""
+    mb = 16 if name == "dlrm_rm3_like" else 200
+    c = make_case(name, num_batches=1, max_batch=mb)
+    with _engine(c, precision="tf32x3") as eng:
+        for B in (mb, 3):
+            dense, ids, lengths = request(c, 0, B)
+            st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+            out, _ = eng.infer(dense, ids, lengths, B)
+            np.testing.assert_allclose(out, st["out"], rtol=1e-4, atol=1e-5)
+            _check_stages(c, eng, st, B, fc_atol=5e-5, fc_rtol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["dlrm_cat", "wnd", "dlrm_rm3_like"])
+def test_tf32_single_pass_throughput_mode(name):
+    """single-pass TF32 (10-bit mantissa operands): atol 2e-3 on post-sigmoid outputs."""
+    mb = 16 if name == "dlrm_rm3_like" else 200
+    c = make_case(name, num_batches=1, max_batch=mb)
+    with _engine(c, precision="tf32") as eng:
+        dense, ids, lengths = request(c, 0, mb)
+        st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+        out, _ = eng.infer(dense, ids, lengths, mb)
+        np.testing.assert_allclose(out, st["out"], rtol=0, atol=2e-3)
+        pooled = eng.fetch_stage(_lib.STAGE_POOLED)
+        assert np.array_equal(pooled.view(np.uint32), st["pooled"].view(np.uint32))
