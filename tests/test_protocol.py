@@ -1,0 +1,189 @@
+"""Queue-protocol tests of the drop-in accel engine.
+
+Tier 1 (always): drive ``accelInferenceEngine`` directly with multiprocessing
+queues and a fake backend — ready token after init, one response per request
+with the reference's fields, sentinel forwarding, failure behaviour.
+
+Tier 2 (authoring container only, /root/reference mounted): the UNMODIFIED
+reference DeepRecSys.py + loadGenerator.py + scheduler.py run a --model_accel
+system experiment against our engine (symlinked next to shims), and the
+outputs dumped by the accel engine match what the CPU oracle computes for the
+same (batch_id, batch_size) — i.e. both processes regenerated identical data
+and parameters from the seed.
+"""
+import glob
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import textwrap
+import time
+
+import numpy as np
+import pytest
+
+from deeprecsys_b200 import accelInferenceEngine as accel_mod
+from deeprecsys_b200.utils.packets import ServiceRequest
+from deeprecsys_b200.utils.utils import cli
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+SMALL_SYSTEM = ["--arch_embedding_size", "500-600-700-800", "--arch_sparse_feature_size", "16",
+                "--arch_mlp_bot", "13-24-16", "--arch_mlp_top", "32-8-1",
+                "--arch_interaction_op", "cat", "--num_indices_per_lookup", "10",
+                "--model_name", "rm1", "--num_batches", "6", "--max_mini_batch_size", "64"]
+
+
+class FakeBackend(object):
+    dump_dir = None
+    built = 0
+
+    def __init__(self, args):
+        type(self).built += 1
+        self.out_dim = 1
+
+    def serve(self, batch_id, batch_size):
+        if batch_id == 3:
+            raise RuntimeError("injected failure")
+        return np.full((batch_size, 1), 0.5, np.float32)
+
+    def close(self):
+        pass
+
+
+class BrokenBackend(object):
+    def __init__(self, args):
+        raise SystemExit("init exploded")
+
+
+def _run_engine(factory, requests, model_name="rm1"):
+    args = cli(SMALL_SYSTEM[:-6] + ["--model_name", model_name, "--num_batches", "6",
+                                    "--max_mini_batch_size", "64"])
+    ctx = mp.get_context("fork")
+    rq, resp, ready = ctx.Queue(), ctx.Queue(), ctx.Queue()
+    old = accel_mod.BACKEND_FACTORY
+    accel_mod.BACKEND_FACTORY = factory
+    try:
+        p = ctx.Process(target=accel_mod.accelInferenceEngine, args=(args, rq, 7, resp, ready))
+        p.daemon = True
+        p.start()
+    finally:
+        accel_mod.BACKEND_FACTORY = old
+    assert ready.get(timeout=60) is True
+    for r in requests:
+        rq.put(r)
+    rq.put(None)
+    out = []
+    while True:
+        item = resp.get(timeout=60)
+        if item is None:
+            break
+        out.append(item)
+    p.join(timeout=30)
+    assert not p.is_alive()
+    return out
+
+
+def _req(batch_id, size, epoch=0, sub_id=0):
+    return ServiceRequest(batch_id=batch_id, epoch=epoch, arrival_time=time.time(),
+                          batch_size=size, sub_id=sub_id, total_sub_batches=1, exp_packet=False)
+
+
+def test_engine_protocol_one_response_per_request_then_sentinel():
+    reqs = [_req(0, 5), _req(1, 64), _req(2, 1, epoch=1)]
+    out = _run_engine(FakeBackend, reqs)
+    assert len(out) == 3
+    for r, q in zip(out, reqs):
+        assert (r.consumer_id, r.epoch, r.batch_id, r.batch_size) == (7, q.epoch, q.batch_id,
+                                                                      q.batch_size)
+        assert r.arrival_time == q.arrival_time
+        assert r.out_batch_size == q.batch_size
+        assert r.total_sub_batches == 1 and r.sub_id == 0 and r.exp_packet is False
+        assert r.queue_start_time <= r.queue_end_time == r.inference_end_time
+        assert r.inference_end_time >= r.arrival_time
+
+
+def test_engine_keeps_serving_after_a_failed_request():
+    out = _run_engine(FakeBackend, [_req(3, 8), _req(4, 8)])
+    assert [r.out_batch_size for r in out] == [0, 8]
+
+
+def test_engine_never_dies_silently_when_init_fails():
+    out = _run_engine(BrokenBackend, [_req(0, 4), _req(1, 4)])
+    assert [r.out_batch_size for r in out] == [0, 0]          # answered, parent can terminate
+
+
+def test_engine_unsupported_model_still_terminates():
+    out = _run_engine(FakeBackend, [_req(0, 4)], model_name="dien")
+    assert [r.out_batch_size for r in out] == [0]
+
+
+def test_engine_without_queue_exits_like_the_reference():
+    args = cli(SMALL_SYSTEM)
+    with pytest.raises(SystemExit):
+        accel_mod.accelInferenceEngine(args)
+
+
+def test_real_backend_fails_loudly_without_gpu_or_library(monkeypatch):
+    """No CPU fallback: on a box without CUDA the real backend raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    args = cli(SMALL_SYSTEM)
+    with pytest.raises(Exception):
+        accel_mod.AccelBackend(args)
+
+
+# ------------------------------------------------------------------ tier 2
+SHIM_ACCEL = """
+from deeprecsys_b200 import accelInferenceEngine as _m
+from oracle.cpu_inference_engine import OracleBackend
+_m.BACKEND_FACTORY = OracleBackend        # CPU test tier only: no GPU here
+accelInferenceEngine = _m.accelInferenceEngine
+"""
+SHIM_CPU = "from oracle.cpu_inference_engine import inferenceEngine\n"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_path):
+    stage = tmp_path / "drs"
+    stage.mkdir()
+    for name in ("DeepRecSys.py", "loadGenerator.py", "scheduler.py", "utils"):
+        os.symlink(os.path.join(REF, name), stage / name)
+    (stage / "accelInferenceEngine.py").write_text(textwrap.dedent(SHIM_ACCEL))
+    (stage / "inferenceEngine.py").write_text(SHIM_CPU)
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    env = dict(os.environ, PYTHONPATH=ROOT, DRS_ACCEL_DUMP_DIR=str(dump), PYTHONWARNINGS="ignore")
+    argv = SMALL_SYSTEM + ["--queue", "--model_accel", "--inference_engines", "1",
+                           "--nepochs", "2", "--batch_size_distribution", "normal",
+                           "--avg_mini_batch_size", "32", "--var_mini_batch_size", "16",
+                           "--sub_task_batch_size", "16", "--accel_request_size_thres", "32",
+                           "--avg_arrival_rate", "3", "--log_file", "log/out.log"]
+    # run the reference script by path (a symlinked script would put /root/reference, not the
+    # staging dir, first on sys.path)
+    launcher = ("import sys, runpy; sys.path.insert(0, '.'); sys.argv = ['DeepRecSys.py'] + %r; "
+                "runpy.run_path('DeepRecSys.py', run_name='__main__')" % (argv,))
+    proc = subprocess.run([sys.executable, "-c", launcher], cwd=str(stage), env=env,
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    out = proc.stdout
+    assert proc.returncode == 0, out[-3000:]
+    assert "Joined  2  inference engines" in out, out[-3000:]
+    assert "Measured QPS" in out and "Measured p99 tail-latency" in out
+    line = [l for l in out.splitlines() if l.startswith("Accel requests")][0]
+    n_accel = int(line.split()[2])
+    assert n_accel > 0
+    dumps = sorted(glob.glob(str(dump / "*.npy")))
+    assert len(dumps) > 0
+    # the accel process regenerated the same data/parameters as an independent CPU restatement
+    from oracle.cpu_inference_engine import OracleBackend
+    args = cli(argv)
+    ref = OracleBackend(args)
+    for path in dumps[:4]:
+        _, e, b, n = os.path.basename(path)[:-4].split("_")
+        got = np.load(path)
+        want = ref.serve(int(b[1:]), int(n[1:]))
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    log = (stage / "log" / "out.log").read_text()
+    assert "'consumer_id': 1" in log          # accel engine = last engine slot
