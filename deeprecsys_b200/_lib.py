@@ -38,7 +38,7 @@ class Spec(C.Structure):
         ("n_top", C.c_int32), ("ln_top", C.POINTER(C.c_int32)),
         ("interaction_op", C.c_int32), ("interaction_itself", C.c_int32),
         ("max_batch", C.c_int32), ("max_lookups_per_table", C.c_int32),
-        ("precision", C.c_int32), ("reserved", C.c_int32),
+        ("precision", C.c_int32), ("n_lanes", C.c_int32),
     ]
 
 

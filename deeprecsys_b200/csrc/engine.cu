@@ -5,9 +5,20 @@
 //   WnD   models/wide_and_deep.py:281-305
 //   NCF   models/ncf.py:198-346
 //   DIN   models/din.py:246-331
-// but executes as: [lengths->offsets] -> bottom MLP -> K1 gather(+cat|dot) ->
-// top MLP on one CUDA stream, all activations resident in HBM buffers owned by
-// the engine.  No CPU fallback: every compute entry point launches kernels.
+// and executes as  [lengths->offsets] -> bottom MLP -> K1 gather(+cat|dot) -> top MLP.
+//
+// Execution resources are organised in LANES: a lane = one CUDA stream + one set
+// of activation buffers + one host-path input slot.  Consecutive queries go to
+// alternating lanes, so the H2D copy and the (latency-bound) MLP kernels of one
+// query overlap the (HBM-bound) gather of the next.  Parameters and staged
+// batches are shared by all lanes.
+//
+// Multi-GPU (one process per GPU): replica mode needs nothing here; table-wise
+// sharding is drs_shard_export/connect — K1 stores pooled vectors directly into
+// the owning rank's buffer through CUDA-IPC peer mappings (NVLink), ordered by the
+// flag barrier of shard.cuh.
+//
+// No CPU fallback: every compute entry point launches kernels.
 #include "../../include/drs_b200.h"
 
 #include <cuda_runtime.h>
@@ -15,6 +26,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -24,6 +36,7 @@
 #include "interact.cuh"
 #include "mlp_ffma.cuh"
 #include "mlp_tc.cuh"
+#include "shard.cuh"
 #include "sls_gather.cuh"
 
 using namespace drs;
@@ -63,15 +76,16 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------ engine
 namespace {
 
-struct Layer {
-  float* W = nullptr;   // [n_units, out, in]
-  float* b = nullptr;   // [n_units, out]
-  float* Wsplit = nullptr;  // tensor-core path: [n_units][2][out][in] = (top-19-bit part, remainder)
+constexpr int kMaxLanes = 4;
+
+struct Layer {                // parameters of one FC layer (shared by all lanes)
+  float* W = nullptr;         // [n_units, out, in]
+  float* b = nullptr;         // [n_units, out]
+  float* Wsplit = nullptr;    // tensor-core path: [n_units][2][out][in] = (top-19-bit part, remainder)
   int out = 0, in = 0;
   int n_units = 1;
   int act = kActRelu;
   std::vector<char> loaded;   // per unit
-  float* y = nullptr;   // own output buffer [n_units, max_batch, out] unless redirected
 };
 
 struct Mlp {
@@ -89,13 +103,34 @@ struct InputSet {                 // one query's inputs in HBM
   int32_t* idx = nullptr;         // slab; table t at idx + idx_pos[t]
   int32_t* lengths = nullptr;     // [T, n]
   int32_t* off = nullptr;         // [T, n+1]
-  int64_t* idx64 = nullptr;       // scratch for int64 uploads (host path only)
-  SlsTableDesc* descs = nullptr;  // [T] device
+  int64_t* idx64 = nullptr;       // scratch for int64 uploads
+  SlsTableDesc* descs = nullptr;  // [T_owned] device (gather descriptors of the owned tables)
   ScanTableDesc* scan = nullptr;  // [T] device
   std::vector<int64_t> idx_pos;   // per table start (ints, multiple of 4)
   std::vector<int64_t> idx_cap;   // per table capacity (ints)
   int n = 0;                      // samples capacity / staged count
-  bool valid = false;
+  int dense_rows = 0;             // rows in `dense`
+  int64_t dense_row0 = 0;         // global sample index of dense row 0 (sharded: slice start)
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tail = nullptr;
+  InputSet slot;                  // host-path inputs
+  float* G = nullptr;             // gather output: R (DLRM-cat, WnD) or P (others); lives in the slab
+  float* R = nullptr;             // top-MLP input [cap_rows, ld_R]
+  float* P = nullptr;             // pooled [cap_rows, T*D]
+  float* dense_out = nullptr;     // DLRM-dot: bottom output
+  float* F = nullptr;             // NCF: [cap_rows, D + tower_out]
+  float* C = nullptr;             // DIN: [n_units, cap_rows, 3D]
+  std::vector<float*> ybot, ytop, yfin;   // per-layer outputs
+  float* out = nullptr;
+  int* d_err = nullptr;
+  int* h_err = nullptr;           // pinned
+  const InputSet* last_inputs = nullptr;
+  int last_B = 0, last_rows = 0;
+  uint32_t epoch = 0;             // sharded exchange epoch on this lane
 };
 
 }  // namespace
@@ -105,30 +140,20 @@ struct drs_engine {
   std::vector<int64_t> table_rows;
   std::vector<int32_t> ln_bot, ln_top;
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_timer[2] = {nullptr, nullptr};
 
-  int T = 0, D = 0, m_den = 0, out_dim = 0, ld_R = 0, n_units = 0;
+  int T = 0, D = 0, m_den = 0, out_dim = 0, ld_R = 0, ld_G = 0, n_units = 0;
+  bool gather_into_R = false, dot = false;
   std::vector<float*> tables;
   std::vector<char> table_loaded;
   Mlp bot, top, fin;          // DIN: bot = attention MLP batched over n_units
 
-  // activations
-  float* R = nullptr;         // top-MLP input [maxB, ld_R]
-  float* P = nullptr;         // pooled [maxB, T*D] (models that need it / dot tap)
-  float* dense_out = nullptr; // DLRM-dot: bottom output [maxB, D]
-  float* F = nullptr;         // NCF: [maxB, D + ln_top[-2]]
-  float* C = nullptr;         // DIN: [n_units, maxB, 3D]
-  float* out = nullptr;       // [maxB, out_dim] (alias of last layer's y)
+  int n_lanes = 2;
+  Lane lanes[kMaxLanes];
+  int next_lane = 0, last_lane = 0;
+  cudaEvent_t ev_timer[2] = {nullptr, nullptr};
 
   std::map<int, InputSet> staged;
-  InputSet slot;              // host-path inputs
-  const InputSet* last_inputs = nullptr;
-  int last_B = 0;
 
-  int* d_err = nullptr;
-  int* h_err = nullptr;       // pinned
   int64_t launches = 0;
   int64_t hbm_bytes = 0;
 
@@ -136,8 +161,17 @@ struct drs_engine {
   int lpr = 0, SB = 1, idx_cap = 0;
   size_t sls_smem = 0;
 
+  // exchange slab: gather-output buffers of all lanes + flag arrays (one IPC handle)
+  unsigned char* slab = nullptr;
+  size_t slab_bytes = 0;
+  size_t lane_G_off[kMaxLanes] = {0, 0, 0, 0};
+  size_t flags_off = 0;       // uint32 [lanes][2][kMaxShardRanks]: arrived, consumed
+  int rank = 0, world = 1;
+  unsigned char* peer_slab[kMaxShardRanks] = {nullptr};
+  std::vector<int> owned;     // tables owned by this rank (all tables when world == 1)
+
   // per-segment CUDA-event profiling (drs_profile_begin/end)
-  std::vector<cudaEvent_t> prof_ev;   // 4 per step: start, after pre-gather, after gather, end
+  std::vector<cudaEvent_t> prof_ev;   // 4 per step: start, before gather, after gather, end
   int prof_cap = 0, prof_n = 0;
   bool prof_on = false;
 };
@@ -156,8 +190,15 @@ int dev_alloc_t(drs_engine* e, T** p, size_t count) {
   return dev_alloc(e, reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
-int alloc_mlp_buffers(drs_engine* e, Mlp& m, const std::vector<int32_t>& ln, int n_units,
-                      int last_act) {
+cudaStream_t s0(drs_engine* e) { return e->lanes[0].stream; }
+
+int sync_all(drs_engine* e) {
+  for (int i = 0; i < e->n_lanes; ++i) CU(cudaStreamSynchronize(e->lanes[i].stream));
+  return DRS_OK;
+}
+
+int alloc_mlp_params(drs_engine* e, Mlp& m, const std::vector<int32_t>& ln, int n_units,
+                     int last_act) {
   const int nl = (int)ln.size() - 1;
   m.layers.resize(nl > 0 ? nl : 0);
   for (int i = 0; i < nl; ++i) {
@@ -171,15 +212,23 @@ int alloc_mlp_buffers(drs_engine* e, Mlp& m, const std::vector<int32_t>& ln, int
     TRY(dev_alloc_t(e, &l.b, (size_t)n_units * l.out));
     if (e->spec.precision != DRS_PREC_FP32)
       TRY(dev_alloc_t(e, &l.Wsplit, (size_t)n_units * 2 * l.out * l.in));
-    TRY(dev_alloc_t(e, &l.y, (size_t)n_units * e->spec.max_batch * l.out));
   }
   return DRS_OK;
 }
 
-int alloc_input_set(drs_engine* e, InputSet& s, int n, const std::vector<int64_t>& idx_counts,
-                    bool with_i64_scratch) {
+int alloc_mlp_acts(drs_engine* e, const Mlp& m, std::vector<float*>& y) {
+  y.assign(m.layers.size(), nullptr);
+  for (size_t i = 0; i < m.layers.size(); ++i)
+    TRY(dev_alloc_t(e, &y[i], (size_t)m.layers[i].n_units * e->spec.max_batch * m.layers[i].out));
+  return DRS_OK;
+}
+
+int alloc_input_set(drs_engine* e, InputSet& s, int n, int dense_rows,
+                    const std::vector<int64_t>& idx_counts, bool with_i64_scratch,
+                    cudaStream_t stream) {
   const int T = e->T;
   s.n = n;
+  s.dense_rows = dense_rows;
   s.idx_pos.assign(T, 0);
   s.idx_cap.assign(T, 0);
   int64_t pos = 0;
@@ -188,9 +237,9 @@ int alloc_input_set(drs_engine* e, InputSet& s, int n, const std::vector<int64_t
     s.idx_cap[t] = idx_counts[t];
     pos += ((idx_counts[t] + 3) & ~int64_t(3)) + 4;   // 16-B aligned starts, TMA over-read pad
   }
-  if (e->m_den > 0) TRY(dev_alloc_t(e, &s.dense, (size_t)n * e->m_den));
+  if (e->m_den > 0) TRY(dev_alloc_t(e, &s.dense, (size_t)dense_rows * e->m_den));
   TRY(dev_alloc_t(e, &s.idx, (size_t)pos + 4));
-  CU(cudaMemsetAsync(s.idx, 0, ((size_t)pos + 4) * sizeof(int32_t), e->stream));
+  CU(cudaMemsetAsync(s.idx, 0, ((size_t)pos + 4) * sizeof(int32_t), stream));
   if (with_i64_scratch) TRY(dev_alloc_t(e, &s.idx64, (size_t)pos + 4));
   TRY(dev_alloc_t(e, &s.lengths, (size_t)T * n));
   TRY(dev_alloc_t(e, &s.off, (size_t)T * (n + 1)));
@@ -207,38 +256,51 @@ void free_input_set(InputSet& s) {
 
 // destination column of table t's pooled vector inside the gather's output buffer
 int gather_dst_col(const drs_engine* e, int t) {
-  switch (e->spec.model_type) {
-    case DRS_MODEL_DLRM: return e->D + t * e->D;           // R = [bot_out, e_0 .. e_{T-1}]
-    case DRS_MODEL_WND:  return e->m_den + t * e->D;       // R = [dense_in, e_0 ..]
-    default:             return t * e->D;                  // P = [e_0 .. e_{T-1}]
-  }
+  if (e->gather_into_R)
+    return (e->spec.model_type == DRS_MODEL_DLRM ? e->D : e->m_den) + t * e->D;
+  return t * e->D;                                         // P = [e_0 .. e_{T-1}]
 }
 
-int write_descs(drs_engine* e, InputSet& s, const std::vector<int64_t>& n_idx) {
-  std::vector<SlsTableDesc> d(e->T);
+bool owns(const drs_engine* e, int t) { return e->world == 1 || (t % e->world) == e->rank; }
+
+int write_descs(drs_engine* e, InputSet& s, const std::vector<int64_t>& n_idx,
+                cudaStream_t stream) {
+  std::vector<SlsTableDesc> d;
   std::vector<ScanTableDesc> sc(e->T);
   for (int t = 0; t < e->T; ++t) {
-    d[t].rows = e->tables[t];
-    d[t].idx = s.idx + s.idx_pos[t];
-    d[t].off = s.off + (size_t)t * (s.n + 1);
-    d[t].n_rows = e->table_rows[t];
-    d[t].dst_col = gather_dst_col(e, t);
-    d[t].pad_ = 0;
+    if (owns(e, t)) {
+      SlsTableDesc x{};
+      x.rows = e->tables[t];
+      x.idx = s.idx + s.idx_pos[t];
+      x.off = s.off + (size_t)t * (s.n + 1);
+      x.n_rows = e->table_rows[t];
+      x.dst_col = gather_dst_col(e, t);
+      x.pad_ = t;
+      d.push_back(x);
+    }
     sc[t].lengths = s.lengths + (size_t)t * s.n;
     sc[t].off = s.off + (size_t)t * (s.n + 1);
     sc[t].n_idx = n_idx.empty() ? -1 : n_idx[t];
   }
-  // pageable -> device copies of small structs are staged by the runtime before returning
-  CU(cudaMemcpyAsync(s.descs, d.data(), d.size() * sizeof(SlsTableDesc), cudaMemcpyHostToDevice,
-                     e->stream));
+  if (!d.empty())
+    CU(cudaMemcpyAsync(s.descs, d.data(), d.size() * sizeof(SlsTableDesc), cudaMemcpyHostToDevice,
+                       stream));
   CU(cudaMemcpyAsync(s.scan, sc.data(), sc.size() * sizeof(ScanTableDesc), cudaMemcpyHostToDevice,
-                     e->stream));
+                     stream));
+  CU(cudaStreamSynchronize(stream));     // the host vectors die here
+  return DRS_OK;
+}
+
+int rewrite_all_descs(drs_engine* e) {
+  for (int i = 0; i < e->n_lanes; ++i) TRY(write_descs(e, e->lanes[i].slot, {}, s0(e)));
+  for (auto& kv : e->staged) TRY(write_descs(e, kv.second, {}, s0(e)));
   return DRS_OK;
 }
 
 // ------------------------------------------------------------ launchers
-int launch_fc(drs_engine* e, const Layer& l, const float* X, int64_t ldx, int64_t x_bstride,
-              int64_t x_rows_total, float* Y, int64_t ldy, int64_t y_bstride, int M) {
+int launch_fc(drs_engine* e, Lane& ln, const Layer& l, const float* X, int64_t ldx,
+              int64_t x_bstride, int64_t x_rows_total, float* Y, int64_t ldy, int64_t y_bstride,
+              int M) {
   if (M <= 0) return DRS_OK;
   if (e->spec.precision != DRS_PREC_FP32 && l.Wsplit && tc_fc_supported(l.out, l.in, ldx, X) &&
       (l.n_units == 1 || x_bstride % ldx == 0)) {
@@ -250,7 +312,7 @@ int launch_fc(drs_engine* e, const Layer& l, const float* X, int64_t ldx, int64_
     q.Y = Y; q.ldy = ldy; q.y_bstride = y_bstride;
     q.M = M; q.N = l.out; q.K = l.in; q.act = l.act;
     q.split3 = (e->spec.precision == DRS_PREC_TF32X3);
-    int rc = tc_fc_launch(q, l.n_units, e->stream);
+    int rc = tc_fc_launch(q, l.n_units, ln.stream);
     if (rc != 0) return fail(DRS_ERR_CUDA, "tensor-core FC launch failed: %s",
                              cudaGetErrorString((cudaError_t)rc));
     e->launches += 1;
@@ -265,54 +327,55 @@ int launch_fc(drs_engine* e, const Layer& l, const float* X, int64_t ldx, int64_
   dim3 grid(ceil_div(p.N, kFcBN), ceil_div(p.M, kFcBM), l.n_units);
   const bool vec = (l.in % 4 == 0) && (ldx % 4 == 0) && (x_bstride % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  if (vec) k_fc_ffma<true><<<grid, kFcThreads, 0, e->stream>>>(p);
-  else     k_fc_ffma<false><<<grid, kFcThreads, 0, e->stream>>>(p);
+  if (vec) k_fc_ffma<true><<<grid, kFcThreads, 0, ln.stream>>>(p);
+  else     k_fc_ffma<false><<<grid, kFcThreads, 0, ln.stream>>>(p);
   CU(cudaGetLastError());
   e->launches += 1;
   return DRS_OK;
 }
 
 // chain an MLP; the last layer may be redirected into a column block of a wider buffer
-int run_mlp(drs_engine* e, Mlp& m, const float* X, int64_t ldx, int64_t x_rows_total, int M,
-            float* last_y = nullptr, int64_t last_ldy = 0) {
+int run_mlp(drs_engine* e, Lane& ln, Mlp& m, std::vector<float*>& ys, const float* X, int64_t ldx,
+            int64_t x_rows_total, int M, float* last_y = nullptr, int64_t last_ldy = 0) {
   const int nl = (int)m.layers.size();
   const float* in = X;
   int64_t ld_in = ldx, bs_in = 0, rows_in = x_rows_total;
   for (int i = 0; i < nl; ++i) {
     Layer& l = m.layers[i];
-    float* y = l.y;
+    float* y = ys[i];
     int64_t ldy = l.out, bsy = (int64_t)e->spec.max_batch * l.out;
     if (i == nl - 1 && last_y) { y = last_y; ldy = last_ldy; bsy = 0; }
-    TRY(launch_fc(e, l, in, ld_in, bs_in, rows_in, y, ldy, bsy, M));
+    TRY(launch_fc(e, ln, l, in, ld_in, bs_in, rows_in, y, ldy, bsy, M));
     in = y; ld_in = ldy; bs_in = bsy; rows_in = e->spec.max_batch;
   }
   return DRS_OK;
 }
 
 template <int LPR, bool DOT>
-int launch_gather_t(drs_engine* e, const SlsLaunch& p, int grid, size_t smem) {
+int launch_gather_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid, size_t smem) {
   static bool attr_set = false;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(k_sls_gather<LPR, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             160 * 1024));
     attr_set = true;
   }
-  k_sls_gather<LPR, DOT><<<grid, kSlsThreads, smem, e->stream>>>(p);
+  k_sls_gather<LPR, DOT><<<grid, kSlsThreads, smem, st>>>(p);
   CU(cudaGetLastError());
   e->launches += 1;
   return DRS_OK;
 }
 
 template <bool DOT>
-int launch_gather_lpr(drs_engine* e, const SlsLaunch& p, int lpr, int grid, size_t smem) {
+int launch_gather_lpr(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
+                      size_t smem) {
   switch (lpr) {
-    case 1:  return launch_gather_t<1, DOT>(e, p, grid, smem);
-    case 2:  return launch_gather_t<2, DOT>(e, p, grid, smem);
-    case 4:  return launch_gather_t<4, DOT>(e, p, grid, smem);
-    case 8:  return launch_gather_t<8, DOT>(e, p, grid, smem);
-    case 16: return launch_gather_t<16, DOT>(e, p, grid, smem);
-    case 32: return launch_gather_t<32, DOT>(e, p, grid, smem);
-    default: return launch_gather_t<0, DOT>(e, p, grid, smem);
+    case 1:  return launch_gather_t<1, DOT>(e, st, p, grid, smem);
+    case 2:  return launch_gather_t<2, DOT>(e, st, p, grid, smem);
+    case 4:  return launch_gather_t<4, DOT>(e, st, p, grid, smem);
+    case 8:  return launch_gather_t<8, DOT>(e, st, p, grid, smem);
+    case 16: return launch_gather_t<16, DOT>(e, st, p, grid, smem);
+    case 32: return launch_gather_t<32, DOT>(e, st, p, grid, smem);
+    default: return launch_gather_t<0, DOT>(e, st, p, grid, smem);
   }
 }
 
@@ -336,26 +399,32 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
   *smem_out = sls_smem_bytes(T, SB, idx_cap, D, dot);
 }
 
-int launch_gather(drs_engine* e, const InputSet& s, int B, float* out, int64_t ld_out, bool dot,
-                  float* pooled_tap) {
+int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
   SlsLaunch p{};
-  p.tables = s.descs; p.T = e->T; p.B = B; p.D = e->D;
-  p.out = out; p.ld_out = ld_out;
+  p.tables = s.descs; p.T = (int)e->owned.size(); p.B = B; p.D = e->D;
+  p.out = ln.G; p.ld_out = e->ld_G;
   p.SB = e->SB; p.idx_cap = e->idx_cap;
-  p.err_flag = e->d_err;
-  p.dense = e->dense_out; p.ld_dense = e->D;
+  p.err_flag = ln.d_err;
+  p.dense = ln.dense_out; p.ld_dense = e->D;
   p.itself = e->spec.interaction_itself;
-  p.pooled_tap = pooled_tap;
-  bool vec = (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  p.pooled_tap = dot ? ln.P : nullptr;
+  bool vec = (e->ld_G % 4 == 0) && ((reinterpret_cast<uintptr_t>(ln.G) & 15) == 0);
   for (int t = 0; t < e->T && vec; ++t) vec = (gather_dst_col(e, t) % 4 == 0);
   p.vec_store = vec ? 1 : 0;
+  if (e->world > 1) {
+    p.shard_S = ceil_div(B, e->world);
+    const int li = (int)(&ln - e->lanes);
+    for (int q = 0; q < e->world; ++q)
+      p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_G_off[li]);
+  }
+  if (p.T == 0) return DRS_OK;
   const int grid = ceil_div(B, e->SB);
-  if (dot) return launch_gather_lpr<true>(e, p, e->lpr, grid, e->sls_smem);
-  return launch_gather_lpr<false>(e, p, e->lpr, grid, e->sls_smem);
+  if (dot) return launch_gather_lpr<true>(e, ln.stream, p, e->lpr, grid, e->sls_smem);
+  return launch_gather_lpr<false>(e, ln.stream, p, e->lpr, grid, e->sls_smem);
 }
 
-int launch_scan(drs_engine* e, const InputSet& s, int B) {
-  k_lengths_to_offsets<<<e->T, kScanThreads, 0, e->stream>>>(s.scan, B, e->d_err);
+int launch_scan(drs_engine* e, cudaStream_t st, const InputSet& s, int B, int* d_err) {
+  k_lengths_to_offsets<<<e->T, kScanThreads, 0, st>>>(s.scan, B, d_err);
   CU(cudaGetLastError());
   e->launches += 1;
   return DRS_OK;
@@ -368,10 +437,36 @@ int ew_grid(int64_t n) {
   return (int)g;
 }
 
+// ------------------------------------------------------------ sharded exchange
+uint32_t* flag_ptr(drs_engine* e, int q, int lane, int which) {   // which: 0 arrived, 1 consumed
+  return reinterpret_cast<uint32_t*>(e->peer_slab[q] + e->flags_off) +
+         ((size_t)lane * 2 + which) * kMaxShardRanks;
+}
+
+int shard_signal(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
+  ShardFlags f{};
+  const int li = (int)(&ln - e->lanes);
+  for (int q = 0; q < e->world; ++q) f.peer_flags[q] = flag_ptr(e, q, li, which);
+  f.world = e->world; f.rank = e->rank;
+  k_shard_signal<<<1, 32, 0, ln.stream>>>(f, epoch);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return DRS_OK;
+}
+
+int shard_wait(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
+  const int li = (int)(&ln - e->lanes);
+  k_shard_wait<<<1, 32, 0, ln.stream>>>(flag_ptr(e, e->rank, li, which), e->world, epoch);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return DRS_OK;
+}
+
 // ------------------------------------------------------------ model graphs
 int check_ready(drs_engine* e) {
   for (int t = 0; t < e->T; ++t)
-    if (!e->table_loaded[t]) return fail(DRS_ERR_STATE, "embedding table %d not loaded", t);
+    if (owns(e, t) && !e->table_loaded[t])
+      return fail(DRS_ERR_STATE, "embedding table %d not loaded", t);
   if (!e->bot.all_loaded()) return fail(DRS_ERR_STATE, "bottom/attention MLP weights not loaded");
   if (!e->top.all_loaded()) return fail(DRS_ERR_STATE, "top MLP weights not loaded");
   if (!e->fin.all_loaded()) return fail(DRS_ERR_STATE, "final FC weights not loaded");
@@ -382,93 +477,119 @@ int check_ready(drs_engine* e) {
 #define PROF_MARK(k)                                                              \
   do {                                                                            \
     if (e->prof_on && e->prof_n < e->prof_cap)                                    \
-      CU(cudaEventRecord(e->prof_ev[(size_t)e->prof_n * 4 + (k)], e->stream));    \
+      CU(cudaEventRecord(e->prof_ev[(size_t)e->prof_n * 4 + (k)], ln.stream));    \
   } while (0)
 
-int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
+// B = samples of the whole query.  Single GPU: rows = B.  Sharded: this rank runs the dense
+// part on its slice [row0, row0 + rows) and gathers its tables for all B samples.
+int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
   const int D = e->D, T = e->T;
+  int row0 = 0, rows = B;
+  if (e->world > 1) {
+    const int S = ceil_div(B, e->world);
+    row0 = e->rank * S;
+    rows = B - row0 < 0 ? 0 : (B - row0 < S ? B - row0 : S);
+    ln.epoch += 1;
+    TRY(shard_wait(e, ln, 1, ln.epoch - 1));   // peers consumed what I wrote last time on this lane
+  }
+  // dense rows of this rank inside s.dense
+  const float* dense = s.dense ? s.dense + (int64_t)(row0 - s.dense_row0) * e->m_den : nullptr;
+  const int64_t dense_rows_left = s.dense_rows - (row0 - s.dense_row0);
+  const int64_t cap = e->spec.max_batch;
   PROF_MARK(0);
   switch (e->spec.model_type) {
     case DRS_MODEL_DLRM: {
-      const bool dot = e->spec.interaction_op == DRS_INTERACT_DOT;
-      if (dot) {
-        TRY(run_mlp(e, e->bot, s.dense, e->m_den, s.n, B, e->dense_out, D));
-        PROF_MARK(1);
-        TRY(launch_gather(e, s, B, e->R, e->ld_R, true, e->P));
-        PROF_MARK(2);
-      } else {
-        TRY(run_mlp(e, e->bot, s.dense, e->m_den, s.n, B, e->R, e->ld_R));
-        PROF_MARK(1);
-        TRY(launch_gather(e, s, B, e->R, e->ld_R, false, nullptr));
-        PROF_MARK(2);
+      if (e->dot) TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows,
+                              ln.dense_out, D));
+      else TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows, ln.R,
+                       e->ld_R));
+      PROF_MARK(1);
+      TRY(launch_gather(e, ln, s, B, e->dot));
+      PROF_MARK(2);
+      if (e->world > 1) {
+        TRY(shard_signal(e, ln, 0, ln.epoch));
+        TRY(shard_wait(e, ln, 0, ln.epoch));
       }
-      TRY(run_mlp(e, e->top, e->R, e->ld_R, e->spec.max_batch, B));
+      TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
     case DRS_MODEL_WND: {
-      k_copy_cols<<<ew_grid((int64_t)B * e->m_den), 256, 0, e->stream>>>(s.dense, e->m_den, e->R,
-                                                                         e->ld_R, B, e->m_den);
-      CU(cudaGetLastError());
-      e->launches += 1;
+      if (rows > 0) {
+        k_copy_cols<<<ew_grid((int64_t)rows * e->m_den), 256, 0, ln.stream>>>(
+            dense, e->m_den, ln.R, e->ld_R, rows, e->m_den);
+        CU(cudaGetLastError());
+        e->launches += 1;
+      }
       PROF_MARK(1);
-      TRY(launch_gather(e, s, B, e->R, e->ld_R, false, nullptr));
+      TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      TRY(run_mlp(e, e->top, e->R, e->ld_R, e->spec.max_batch, B));
+      if (e->world > 1) {
+        TRY(shard_signal(e, ln, 0, ln.epoch));
+        TRY(shard_wait(e, ln, 0, ln.epoch));
+      }
+      TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
     case DRS_MODEL_NCF: {
       const int64_t ldp = (int64_t)T * D;
       const int ldf = D + e->top.layers.back().out;
       PROF_MARK(1);
-      TRY(launch_gather(e, s, B, e->P, ldp, false, nullptr));
+      TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      k_add_cols<<<ew_grid((int64_t)B * D), 256, 0, e->stream>>>(e->P, e->P + D, ldp, e->F, ldf, B,
-                                                                 D);
-      CU(cudaGetLastError());
-      e->launches += 1;
-      TRY(run_mlp(e, e->top, e->P + 2 * D, ldp, e->spec.max_batch, B, e->F + D, ldf));
-      TRY(run_mlp(e, e->fin, e->F, ldf, e->spec.max_batch, B));
+      if (e->world > 1) {
+        TRY(shard_signal(e, ln, 0, ln.epoch));
+        TRY(shard_wait(e, ln, 0, ln.epoch));
+      }
+      if (rows > 0) {
+        k_add_cols<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(ln.P, ln.P + D, ldp, ln.F,
+                                                                      ldf, rows, D);
+        CU(cudaGetLastError());
+        e->launches += 1;
+      }
+      TRY(run_mlp(e, ln, e->top, ln.ytop, ln.P + 2 * D, ldp, cap, rows, ln.F + D, ldf));
+      TRY(run_mlp(e, ln, e->fin, ln.yfin, ln.F, ldf, cap, rows));
       break;
     }
     case DRS_MODEL_DIN: {
       const int64_t ldp = (int64_t)T * D;
       const int nu = e->n_units;
       PROF_MARK(1);
-      TRY(launch_gather(e, s, B, e->P, ldp, false, nullptr));
+      TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      k_din_concat<<<ew_grid((int64_t)nu * B * D), 256, 0, e->stream>>>(
-          e->P, ldp, e->C, (int64_t)e->spec.max_batch * 3 * D, B, D, nu, T - 2);
-      CU(cudaGetLastError());
-      e->launches += 1;
-      // attention MLPs, batched over units (each unit has its own weights)
-      {
+      if (e->world > 1) {
+        TRY(shard_signal(e, ln, 0, ln.epoch));
+        TRY(shard_wait(e, ln, 0, ln.epoch));
+      }
+      if (rows > 0) {
+        k_din_concat<<<ew_grid((int64_t)nu * rows * D), 256, 0, ln.stream>>>(
+            ln.P, ldp, ln.C, cap * 3 * D, rows, D, nu, T - 2);
+        CU(cudaGetLastError());
+        e->launches += 1;
+        // attention MLPs, batched over units (each unit has its own weights)
         const int nl = (int)e->bot.layers.size();
-        const float* in = e->C;
-        int64_t ld_in = 3 * D, bs_in = (int64_t)e->spec.max_batch * 3 * D;
+        const float* in = ln.C;
+        int64_t ld_in = 3 * D, bs_in = cap * 3 * D;
         for (int i = 0; i < nl; ++i) {
           Layer& l = e->bot.layers[i];
-          const int64_t bsy = (int64_t)e->spec.max_batch * l.out;
-          TRY(launch_fc(e, l, in, ld_in, bs_in, (int64_t)nu * e->spec.max_batch, l.y, l.out, bsy,
-                        B));
-          in = l.y; ld_in = l.out; bs_in = bsy;
+          const int64_t bsy = cap * l.out;
+          TRY(launch_fc(e, ln, l, in, ld_in, bs_in, (int64_t)nu * cap, ln.ybot[i], l.out, bsy,
+                        rows));
+          in = ln.ybot[i]; ld_in = l.out; bs_in = bsy;
+        }
+        k_sum_units<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(
+            ln.ybot.back(), cap * D, ln.R + D, e->ld_R, rows, D, nu);
+        CU(cudaGetLastError());
+        e->launches += 1;
+        const int cols[3] = {0, T - 2, T - 1};       // profile, candidate ad, context
+        const int dsts[3] = {0, 2 * D, 3 * D};
+        for (int k = 0; k < 3; ++k) {
+          k_copy_cols<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(
+              ln.P + (int64_t)cols[k] * D, ldp, ln.R + dsts[k], e->ld_R, rows, D);
+          CU(cudaGetLastError());
+          e->launches += 1;
         }
       }
-      {
-        const Layer& last = e->bot.layers.back();
-        k_sum_units<<<ew_grid((int64_t)B * D), 256, 0, e->stream>>>(
-            last.y, (int64_t)e->spec.max_batch * D, e->R + D, e->ld_R, B, D, nu);
-        CU(cudaGetLastError());
-        e->launches += 1;
-      }
-      const int cols[3] = {0, T - 2, T - 1};       // profile, candidate ad, context
-      const int dsts[3] = {0, 2 * D, 3 * D};
-      for (int k = 0; k < 3; ++k) {
-        k_copy_cols<<<ew_grid((int64_t)B * D), 256, 0, e->stream>>>(
-            e->P + (int64_t)cols[k] * D, ldp, e->R + dsts[k], e->ld_R, B, D);
-        CU(cudaGetLastError());
-        e->launches += 1;
-      }
-      TRY(run_mlp(e, e->top, e->R, e->ld_R, e->spec.max_batch, B));
+      TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
     default:
@@ -476,18 +597,21 @@ int enqueue_graph(drs_engine* e, const InputSet& s, int B) {
   }
   PROF_MARK(3);
   if (e->prof_on && e->prof_n < e->prof_cap) e->prof_n += 1;
-  CU(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  e->last_inputs = &s;
-  e->last_B = B;
+  if (e->world > 1) TRY(shard_signal(e, ln, 1, ln.epoch));   // my buffer may be overwritten
+  CU(cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
+  ln.last_inputs = &s;
+  ln.last_B = B;
+  ln.last_rows = rows;
   return DRS_OK;
 }
 
-int finish_sync(drs_engine* e) {
-  CU(cudaStreamSynchronize(e->stream));
-  if (*e->h_err) {
-    *e->h_err = 0;
-    cudaMemsetAsync(e->d_err, 0, sizeof(int), e->stream);
-    cudaStreamSynchronize(e->stream);
+int finish_lane(drs_engine* e, Lane& ln) {
+  (void)e;
+  CU(cudaStreamSynchronize(ln.stream));
+  if (*ln.h_err) {
+    *ln.h_err = 0;
+    cudaMemsetAsync(ln.d_err, 0, sizeof(int), ln.stream);
+    cudaStreamSynchronize(ln.stream);
     return fail(DRS_ERR_INDEX,
                 "SparseLengthsSum enforce failed: index out of range, negative length, or "
                 "sum(lengths) != len(indices)");
@@ -495,17 +619,36 @@ int finish_sync(drs_engine* e) {
   return DRS_OK;
 }
 
-// upload one query into an InputSet (host -> device on the engine stream)
-int upload_inputs(drs_engine* e, InputSet& s, const float* dense, const void* const* idx,
-                  int idx_is_i64, const int32_t* const* lengths, int B,
+int finish_all(drs_engine* e) {
+  int rc = DRS_OK;
+  for (int i = 0; i < e->n_lanes; ++i) {
+    int r = finish_lane(e, e->lanes[i]);
+    if (r != DRS_OK) rc = r;
+  }
+  return rc;
+}
+
+Lane& pick_lane(drs_engine* e) {
+  Lane& ln = e->lanes[e->next_lane];
+  e->last_lane = e->next_lane;
+  e->next_lane = (e->next_lane + 1) % e->n_lanes;
+  return ln;
+}
+
+// upload one query into an InputSet (host -> device on `stream`).  Sharded: ids are uploaded
+// only for owned tables (lengths and dense rows for all: they are small).
+int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* dense,
+                  const void* const* idx, int idx_is_i64, const int32_t* const* lengths, int B,
                   std::vector<int64_t>* n_idx_out) {
   const int T = e->T;
   CHECK_ARG(B >= 0 && B <= s.n, "batch_size %d exceeds capacity %d", B, s.n);
   CHECK_ARG(idx && lengths, "idx/lengths pointer arrays must not be NULL");
-  if (e->m_den > 0) {
+  s.dense_row0 = 0;                    // every rank keeps all dense rows; slices are taken at serve time
+  if (e->m_den > 0 && B > 0) {
     CHECK_ARG(dense != nullptr, "model has %d dense features but dense == NULL", e->m_den);
+    CHECK_ARG(B <= s.dense_rows, "dense rows %d exceed capacity %d", B, s.dense_rows);
     CU(cudaMemcpyAsync(s.dense, dense, (size_t)B * e->m_den * sizeof(float),
-                       cudaMemcpyHostToDevice, e->stream));
+                       cudaMemcpyHostToDevice, stream));
   }
   std::vector<int64_t>& n_idx = *n_idx_out;
   n_idx.assign(T, 0);
@@ -527,15 +670,15 @@ int upload_inputs(drs_engine* e, InputSet& s, const float* dense, const void* co
     len_strided = ((const char*)lengths[t] - (const char*)lengths[t - 1]) == lstride;
   if (len_strided && lstride >= (ptrdiff_t)(B * sizeof(int32_t)) && B > 0) {
     CU(cudaMemcpy2DAsync(s.lengths, (size_t)s.n * sizeof(int32_t), lengths[0], (size_t)lstride,
-                         (size_t)B * sizeof(int32_t), T, cudaMemcpyHostToDevice, e->stream));
+                         (size_t)B * sizeof(int32_t), T, cudaMemcpyHostToDevice, stream));
   } else {
     for (int t = 0; t < T; ++t)
       CU(cudaMemcpyAsync(s.lengths + (size_t)t * s.n, lengths[t], (size_t)B * sizeof(int32_t),
-                         cudaMemcpyHostToDevice, e->stream));
+                         cudaMemcpyHostToDevice, stream));
   }
   const size_t isz = idx_is_i64 ? sizeof(int64_t) : sizeof(int32_t);
   // ids: equal counts + equal host stride + equal device stride -> one 2-D copy
-  bool idx_strided = T > 1 && !idx_is_i64;
+  bool idx_strided = T > 1 && !idx_is_i64 && e->world == 1;
   const ptrdiff_t istride = T > 1 ? (const char*)idx[1] - (const char*)idx[0] : 0;
   const int64_t dstride = T > 1 ? s.idx_pos[1] - s.idx_pos[0] : 0;
   for (int t = 1; t < T && idx_strided; ++t)
@@ -544,25 +687,37 @@ int upload_inputs(drs_engine* e, InputSet& s, const float* dense, const void* co
   if (idx_strided && n_idx[0] > 0 && istride >= (ptrdiff_t)(n_idx[0] * isz)) {
     CU(cudaMemcpy2DAsync(s.idx + s.idx_pos[0], (size_t)dstride * sizeof(int32_t), idx[0],
                          (size_t)istride, (size_t)n_idx[0] * sizeof(int32_t), T,
-                         cudaMemcpyHostToDevice, e->stream));
+                         cudaMemcpyHostToDevice, stream));
   } else {
     for (int t = 0; t < T; ++t) {
-      if (n_idx[t] == 0) continue;
+      if (n_idx[t] == 0 || !owns(e, t)) continue;
       if (idx_is_i64) {
         CU(cudaMemcpyAsync(s.idx64 + s.idx_pos[t], idx[t], (size_t)n_idx[t] * sizeof(int64_t),
-                           cudaMemcpyHostToDevice, e->stream));
-        k_cast_i64_i32<<<ew_grid(n_idx[t]), 256, 0, e->stream>>>(s.idx64 + s.idx_pos[t],
-                                                                 s.idx + s.idx_pos[t], n_idx[t]);
+                           cudaMemcpyHostToDevice, stream));
+        k_cast_i64_i32<<<ew_grid(n_idx[t]), 256, 0, stream>>>(s.idx64 + s.idx_pos[t],
+                                                              s.idx + s.idx_pos[t], n_idx[t]);
         CU(cudaGetLastError());
         e->launches += 1;
       } else {
         CU(cudaMemcpyAsync(s.idx + s.idx_pos[t], idx[t], (size_t)n_idx[t] * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, e->stream));
+                           cudaMemcpyHostToDevice, stream));
       }
     }
   }
   return DRS_OK;
 }
+
+struct ShardBlob {                 // DRS_SHARD_BLOB_BYTES
+  uint32_t magic;
+  int32_t n_lanes;
+  int32_t device;
+  int32_t reserved;
+  uint64_t slab_bytes;
+  uint64_t flags_off;
+  uint64_t lane_G_off[kMaxLanes];
+  cudaIpcMemHandle_t handle;       // 64 bytes
+};
+static_assert(sizeof(ShardBlob) <= DRS_SHARD_BLOB_BYTES, "blob too large");
 
 }  // namespace
 
@@ -597,6 +752,8 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   CHECK_ARG(spec->n_top >= 2 && spec->ln_top, "top MLP needs at least one layer");
   CHECK_ARG(spec->precision >= DRS_PREC_FP32 && spec->precision <= DRS_PREC_TF32,
             "unknown precision %d", spec->precision);
+  CHECK_ARG(spec->n_lanes >= 0 && spec->n_lanes <= kMaxLanes, "n_lanes must be in [0,%d]",
+            kMaxLanes);
   for (int t = 0; t < spec->n_tables; ++t)
     CHECK_ARG(spec->table_rows[t] >= 1 && spec->table_rows[t] < (int64_t(1) << 31),
               "table %d: rows must be in [1, 2^31) (ids are int32 after the Cast)", t);
@@ -610,6 +767,7 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   e->device = device;
   e->T = spec->n_tables;
   e->D = spec->emb_dim;
+  e->n_lanes = spec->n_lanes > 0 ? spec->n_lanes : 2;
   e->table_rows.assign(spec->table_rows, spec->table_rows + spec->n_tables);
   if (spec->n_bot > 0 && spec->ln_bot) e->ln_bot.assign(spec->ln_bot, spec->ln_bot + spec->n_bot);
   e->ln_top.assign(spec->ln_top, spec->ln_top + spec->n_top);
@@ -617,22 +775,27 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   e->spec.ln_bot = e->ln_bot.data();
   e->spec.ln_top = e->ln_top.data();
   const int T = e->T, D = e->D, maxB = spec->max_batch;
+  for (int t = 0; t < T; ++t) e->owned.push_back(t);
 
   auto bail = [&](int rc) { drs_destroy(e); return rc; };
 #define TRYB(expr) do { int rc_ = (expr); if (rc_ != DRS_OK) return bail(rc_); } while (0)
 #define CHECKB(cond, ...) do { if (!(cond)) return bail(fail(DRS_ERR_INVALID, __VA_ARGS__)); } while (0)
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(DRS_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_))); } while (0)
 
-  CUB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  for (auto& v : e->ev) CUB(cudaEventCreate(&v));
+  for (int i = 0; i < e->n_lanes; ++i) {
+    Lane& ln = e->lanes[i];
+    CUB(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    for (auto& v : ln.ev) CUB(cudaEventCreate(&v));
+    CUB(cudaEventCreateWithFlags(&ln.tail, cudaEventDisableTiming));
+    TRYB(dev_alloc_t(e, &ln.d_err, 4));
+    CUB(cudaMemset(ln.d_err, 0, 16));
+    CUB(cudaHostAlloc((void**)&ln.h_err, 16, cudaHostAllocDefault));
+    *ln.h_err = 0;
+  }
   for (auto& v : e->ev_timer) CUB(cudaEventCreate(&v));
-  TRYB(dev_alloc_t(e, &e->d_err, 4));
-  CUB(cudaMemset(e->d_err, 0, 16));
-  CUB(cudaHostAlloc((void**)&e->h_err, 16, cudaHostAllocDefault));
-  *e->h_err = 0;
 
   // --- dims and checks per model (mirroring the reference's sys.exit checks)
-  bool dot = false;
+  int tower_out = 0;
   switch (spec->model_type) {
     case DRS_MODEL_DLRM: {
       CHECKB(e->ln_bot.size() >= 2, "DLRM needs a bottom MLP");
@@ -641,20 +804,17 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
              "arch-sparse-feature-size %d does not match last dim of bottom mlp %d", D,
              e->ln_bot.back());                                  // dlrm_s_caffe2.py:435
       const int F = T + 1;
-      dot = spec->interaction_op == DRS_INTERACT_DOT;
-      CHECKB(dot || spec->interaction_op == DRS_INTERACT_CAT, "interaction op not supported");
-      const int num_int = dot ? (spec->interaction_itself ? F * (F + 1) / 2 : F * (F - 1) / 2) + D
-                              : F * D;                           // :419-424
+      e->dot = spec->interaction_op == DRS_INTERACT_DOT;
+      CHECKB(e->dot || spec->interaction_op == DRS_INTERACT_CAT, "interaction op not supported");
+      const int num_int =
+          e->dot ? (spec->interaction_itself ? F * (F + 1) / 2 : F * (F - 1) / 2) + D : F * D;
       CHECKB(e->ln_top[0] == num_int,
              "# of feature interactions %d does not match first dim of top mlp %d", num_int,
              e->ln_top[0]);                                      // :438
       e->ld_R = num_int;
-      TRYB(alloc_mlp_buffers(e, e->bot, e->ln_bot, 1, kActRelu));       // sigmoid_bot = -1
-      TRYB(alloc_mlp_buffers(e, e->top, e->ln_top, 1, kActSigmoid));    // sigmoid_top = last
-      if (dot) {
-        TRYB(dev_alloc_t(e, &e->dense_out, (size_t)maxB * D));
-        TRYB(dev_alloc_t(e, &e->P, (size_t)maxB * T * D));
-      }
+      e->gather_into_R = true;       // dot: the fused kernel also writes R (and taps P)
+      TRYB(alloc_mlp_params(e, e->bot, e->ln_bot, 1, kActRelu));       // sigmoid_bot = -1
+      TRYB(alloc_mlp_params(e, e->top, e->ln_top, 1, kActSigmoid));    // sigmoid_top = last
       break;
     }
     case DRS_MODEL_WND: {
@@ -663,7 +823,8 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
       CHECKB(e->ln_top[0] == T * D + e->m_den, "top mlp input %d != T*D + m_den = %d",
              e->ln_top[0], T * D + e->m_den);                    // wide_and_deep.py:345
       e->ld_R = e->ln_top[0];
-      TRYB(alloc_mlp_buffers(e, e->top, e->ln_top, 1, kActSigmoid));
+      e->gather_into_R = true;
+      TRYB(alloc_mlp_params(e, e->top, e->ln_top, 1, kActSigmoid));
       break;
     }
     case DRS_MODEL_NCF: {
@@ -672,10 +833,9 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
       e->m_den = 0;
       std::vector<int32_t> tower(e->ln_top.begin(), e->ln_top.end() - 1);   // ncf.py:332
       std::vector<int32_t> fin = {D + tower.back(), e->ln_top.back()};      // :339-343
-      TRYB(alloc_mlp_buffers(e, e->top, tower, 1, kActRelu));
-      TRYB(alloc_mlp_buffers(e, e->fin, fin, 1, kActRelu));
-      TRYB(dev_alloc_t(e, &e->P, (size_t)maxB * T * D));
-      TRYB(dev_alloc_t(e, &e->F, (size_t)maxB * (D + tower.back())));
+      tower_out = tower.back();
+      TRYB(alloc_mlp_params(e, e->top, tower, 1, kActRelu));
+      TRYB(alloc_mlp_params(e, e->fin, fin, 1, kActRelu));
       e->ld_R = 0;
       break;
     }
@@ -687,31 +847,61 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
       e->m_den = 0;
       e->n_units = T - 3;
       e->ld_R = 4 * D;
-      TRYB(alloc_mlp_buffers(e, e->bot, e->ln_bot, e->n_units, kActRelu));
-      TRYB(alloc_mlp_buffers(e, e->top, e->ln_top, 1, kActRelu));
-      TRYB(dev_alloc_t(e, &e->P, (size_t)maxB * T * D));
-      TRYB(dev_alloc_t(e, &e->C, (size_t)e->n_units * maxB * 3 * D));
+      TRYB(alloc_mlp_params(e, e->bot, e->ln_bot, e->n_units, kActRelu));
+      TRYB(alloc_mlp_params(e, e->top, e->ln_top, 1, kActRelu));
       break;
     }
     default:
       return bail(fail(DRS_ERR_INVALID, "unknown model_type %d", spec->model_type));
   }
-  if (e->ld_R > 0) TRYB(dev_alloc_t(e, &e->R, (size_t)maxB * e->ld_R));
+  e->ld_G = e->gather_into_R ? e->ld_R : T * D;
+  const bool dlrm_dot = e->dot;
+
+  // exchange slab: one allocation (one IPC handle) = gather outputs of all lanes + flags
+  {
+    size_t off = 0;
+    const size_t g_bytes = (((size_t)maxB * e->ld_G * sizeof(float)) + 255) & ~size_t(255);
+    for (int i = 0; i < e->n_lanes; ++i) { e->lane_G_off[i] = off; off += g_bytes; }
+    e->flags_off = off;
+    off += (size_t)kMaxLanes * 2 * kMaxShardRanks * sizeof(uint32_t);
+    e->slab_bytes = (off + 255) & ~size_t(255);
+    TRYB(dev_alloc(e, (void**)&e->slab, e->slab_bytes));
+    CUB(cudaMemset(e->slab, 0, e->slab_bytes));
+    e->peer_slab[0] = e->slab;
+  }
+
+  const int64_t max_lk = spec->max_lookups_per_table > 0 ? spec->max_lookups_per_table : maxB;
+  std::vector<int64_t> caps(T, max_lk);
+  for (int i = 0; i < e->n_lanes; ++i) {
+    Lane& ln = e->lanes[i];
+    ln.G = reinterpret_cast<float*>(e->slab + e->lane_G_off[i]);
+    if (e->gather_into_R) ln.R = ln.G; else ln.P = ln.G;
+    if (!e->gather_into_R && e->ld_R > 0) TRYB(dev_alloc_t(e, &ln.R, (size_t)maxB * e->ld_R));
+    if (dlrm_dot) {
+      TRYB(dev_alloc_t(e, &ln.dense_out, (size_t)maxB * D));
+      TRYB(dev_alloc_t(e, &ln.P, (size_t)maxB * T * D));
+    }
+    if (spec->model_type == DRS_MODEL_NCF)
+      TRYB(dev_alloc_t(e, &ln.F, (size_t)maxB * (D + tower_out)));
+    if (spec->model_type == DRS_MODEL_DIN)
+      TRYB(dev_alloc_t(e, &ln.C, (size_t)e->n_units * maxB * 3 * D));
+    TRYB(alloc_mlp_acts(e, e->bot, ln.ybot));
+    TRYB(alloc_mlp_acts(e, e->top, ln.ytop));
+    TRYB(alloc_mlp_acts(e, e->fin, ln.yfin));
+    ln.out = (spec->model_type == DRS_MODEL_NCF) ? ln.yfin.back() : ln.ytop.back();
+    TRYB(alloc_input_set(e, ln.slot, maxB, maxB, caps, true, ln.stream));
+  }
   Mlp& lastm = (spec->model_type == DRS_MODEL_NCF) ? e->fin : e->top;
-  e->out = lastm.layers.back().y;
   e->out_dim = lastm.layers.back().out;
 
   e->tables.assign(T, nullptr);
   e->table_loaded.assign(T, 0);
 
-  const int64_t max_lk = spec->max_lookups_per_table > 0 ? spec->max_lookups_per_table : maxB;
   const int64_t avg_len = ceil_div64(max_lk, maxB);
-  plan_gather(T, D, avg_len, dot, &e->lpr, &e->SB, &e->idx_cap, &e->sls_smem);
+  plan_gather(T, D, avg_len, dlrm_dot, &e->lpr, &e->SB, &e->idx_cap, &e->sls_smem);
 
-  std::vector<int64_t> caps(T, max_lk);
-  TRYB(alloc_input_set(e, e->slot, maxB, caps, true));
-  TRYB(write_descs(e, e->slot, {}));
-  CUB(cudaStreamSynchronize(e->stream));
+  TRYB(rewrite_all_descs(e));
+  TRYB(sync_all(e));
   *out = e;
   return DRS_OK;
 #undef TRYB
@@ -722,19 +912,30 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
 int drs_destroy(drs_engine* e) {
   if (!e) return DRS_OK;
   cudaSetDevice(e->device);
-  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (int i = 0; i < e->n_lanes; ++i)
+    if (e->lanes[i].stream) cudaStreamSynchronize(e->lanes[i].stream);
+  for (int q = 0; q < e->world; ++q)
+    if (q != e->rank && e->peer_slab[q]) cudaIpcCloseMemHandle(e->peer_slab[q]);
   for (float* t : e->tables) cudaFree(t);
   for (Mlp* m : {&e->bot, &e->top, &e->fin})
-    for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wsplit); cudaFree(l.y); }
-  cudaFree(e->R); cudaFree(e->P); cudaFree(e->dense_out); cudaFree(e->F); cudaFree(e->C);
+    for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wsplit); }
   for (auto& kv : e->staged) free_input_set(kv.second);
-  free_input_set(e->slot);
-  cudaFree(e->d_err);
-  if (e->h_err) cudaFreeHost(e->h_err);
-  for (auto& v : e->ev) if (v) cudaEventDestroy(v);
+  for (int i = 0; i < kMaxLanes; ++i) {
+    Lane& ln = e->lanes[i];
+    if (!e->gather_into_R) cudaFree(ln.R);
+    if (e->dot) cudaFree(ln.P);
+    cudaFree(ln.dense_out); cudaFree(ln.F); cudaFree(ln.C);
+    for (auto* v : {&ln.ybot, &ln.ytop, &ln.yfin}) for (float* p : *v) cudaFree(p);
+    free_input_set(ln.slot);
+    cudaFree(ln.d_err);
+    if (ln.h_err) cudaFreeHost(ln.h_err);
+    for (auto& v : ln.ev) if (v) cudaEventDestroy(v);
+    if (ln.tail) cudaEventDestroy(ln.tail);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+  }
+  cudaFree(e->slab);
   for (auto& v : e->ev_timer) if (v) cudaEventDestroy(v);
   for (auto& v : e->prof_ev) cudaEventDestroy(v);
-  if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return DRS_OK;
 }
@@ -752,18 +953,16 @@ int drs_load_table(drs_engine* e, int table, const float* rows, int64_t n_rows, 
             "table %d: got [%lld,%d], spec says [%lld,%d]", table, (long long)n_rows, dim,
             (long long)e->table_rows[table], e->D);
   CU(cudaSetDevice(e->device));
+  TRY(sync_all(e));
   if (!e->tables[table]) {
     // +16 floats of slack keeps 16-B vector loads of the last row in-bounds for any D
     TRY(dev_alloc_t(e, &e->tables[table], (size_t)n_rows * dim + 16));
   }
   CU(cudaMemcpyAsync(e->tables[table], rows, (size_t)n_rows * dim * sizeof(float),
-                     cudaMemcpyHostToDevice, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
+                     cudaMemcpyHostToDevice, s0(e)));
+  CU(cudaStreamSynchronize(s0(e)));
   e->table_loaded[table] = 1;
-  // descriptors hold the table pointers
-  TRY(write_descs(e, e->slot, {}));
-  CU(cudaStreamSynchronize(e->stream));
-  return DRS_OK;
+  return rewrite_all_descs(e);       // descriptors hold the table pointers
 }
 
 int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const float* b, int out_dim,
@@ -786,19 +985,20 @@ int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const floa
   Layer& l = m->layers[layer];
   CHECK_ARG(l.out == out_dim && l.in == in_dim, "mlp %d layer %d: got [%d,%d], spec says [%d,%d]",
             mlp_id, layer, out_dim, in_dim, l.out, l.in);
+  TRY(sync_all(e));
   const size_t wcount = (size_t)l.out * l.in;
   CU(cudaMemcpyAsync(l.W + unit * wcount, W, wcount * sizeof(float), cudaMemcpyHostToDevice,
-                     e->stream));
+                     s0(e)));
   CU(cudaMemcpyAsync(l.b + (size_t)unit * l.out, b, (size_t)l.out * sizeof(float),
-                     cudaMemcpyHostToDevice, e->stream));
+                     cudaMemcpyHostToDevice, s0(e)));
   if (l.Wsplit) {
     int rc = tc_split_weights(l.W + unit * wcount, l.Wsplit + unit * 2 * wcount, (int64_t)wcount,
-                              e->stream);
+                              s0(e));
     if (rc != 0) return fail(DRS_ERR_CUDA, "weight split failed: %s",
                              cudaGetErrorString((cudaError_t)rc));
     e->launches += 1;
   }
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaStreamSynchronize(s0(e)));
   l.loaded[unit] = 1;
   return DRS_OK;
 }
@@ -810,7 +1010,9 @@ int drs_stage_batch(drs_engine* e, int batch_id, const float* dense, const void*
   CHECK_ARG(idx && lengths, "idx/lengths pointer arrays must not be NULL");
   CU(cudaSetDevice(e->device));
   for (int t = 0; t < e->T; ++t)
-    if (!e->table_loaded[t]) return fail(DRS_ERR_STATE, "stage after loading tables (table %d)", t);
+    if (owns(e, t) && !e->table_loaded[t])
+      return fail(DRS_ERR_STATE, "stage after loading tables (table %d)", t);
+  TRY(sync_all(e));
   const int T = e->T;
   std::vector<int64_t> counts(T, 0);
   for (int t = 0; t < T; ++t)
@@ -818,115 +1020,149 @@ int drs_stage_batch(drs_engine* e, int batch_id, const float* dense, const void*
       if (lengths[t][b] < 0) return fail(DRS_ERR_INDEX, "negative length");
       counts[t] += lengths[t][b];
     }
+  std::vector<int64_t> alloc_counts = counts;
+  for (int t = 0; t < T; ++t) if (!owns(e, t)) alloc_counts[t] = 0;
   auto it = e->staged.find(batch_id);
   if (it != e->staged.end()) { free_input_set(it->second); e->staged.erase(it); }
   InputSet s;
-  int rc = alloc_input_set(e, s, n_samples, counts, idx_is_i64 != 0);
+  const int dense_rows = n_samples;
+  Lane& l0 = e->lanes[0];
+  int rc = alloc_input_set(e, s, n_samples, dense_rows, alloc_counts, idx_is_i64 != 0, l0.stream);
   if (rc != DRS_OK) { free_input_set(s); return rc; }
+  for (int t = 0; t < T; ++t) s.idx_cap[t] = counts[t];   // capacity check is on the host counts
   std::vector<int64_t> n_idx;
-  rc = upload_inputs(e, s, dense, idx, idx_is_i64, lengths, n_samples, &n_idx);
-  if (rc == DRS_OK) rc = write_descs(e, s, n_idx);
-  if (rc == DRS_OK) rc = launch_scan(e, s, n_samples);
+  rc = upload_inputs(e, s, l0.stream, dense, idx, idx_is_i64, lengths, n_samples, &n_idx);
+  if (rc == DRS_OK) rc = write_descs(e, s, n_idx, l0.stream);
+  if (rc == DRS_OK) rc = launch_scan(e, l0.stream, s, n_samples, l0.d_err);
   if (rc == DRS_OK) {
-    cudaError_t ce = cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost,
-                                     e->stream);
+    cudaError_t ce = cudaMemcpyAsync(l0.h_err, l0.d_err, sizeof(int), cudaMemcpyDeviceToHost,
+                                     l0.stream);
     if (ce != cudaSuccess) rc = fail(DRS_ERR_CUDA, "%s", cudaGetErrorString(ce));
   }
-  if (rc == DRS_OK) rc = finish_sync(e);
+  if (rc == DRS_OK) rc = finish_lane(e, l0);
   if (rc != DRS_OK) { free_input_set(s); return rc; }
   if (s.idx64) { cudaFree(s.idx64); s.idx64 = nullptr; }
-  s.valid = true;
   e->staged[batch_id] = s;
   return DRS_OK;
 }
 
-int drs_enqueue_staged(drs_engine* e, int batch_id, int batch_size) {
-  CHECK_ARG(e, "engine is NULL");
+static int enqueue_staged_on(drs_engine* e, Lane& ln, int batch_id, int batch_size) {
   auto it = e->staged.find(batch_id);
   if (it == e->staged.end()) return fail(DRS_ERR_STATE, "batch %d was not staged", batch_id);
-  CHECK_ARG(batch_size >= 1 && batch_size <= it->second.n && batch_size <= e->spec.max_batch,
-            "batch_size %d out of range [1, min(%d staged, %d max_batch)]", batch_size,
-            it->second.n, e->spec.max_batch);
+  const int64_t cap = (int64_t)e->spec.max_batch * e->world;
+  CHECK_ARG(batch_size >= 1 && batch_size <= it->second.n && batch_size <= cap,
+            "batch_size %d out of range [1, min(%d staged, %lld max_batch)]", batch_size,
+            it->second.n, (long long)cap);
   CU(cudaSetDevice(e->device));
   TRY(check_ready(e));
-  return enqueue_graph(e, it->second, batch_size);
+  return enqueue_graph(e, ln, it->second, batch_size);
+}
+
+int drs_enqueue_staged(drs_engine* e, int batch_id, int batch_size) {
+  CHECK_ARG(e, "engine is NULL");
+  return enqueue_staged_on(e, pick_lane(e), batch_id, batch_size);
 }
 
 int drs_sync(drs_engine* e) {
   CHECK_ARG(e, "engine is NULL");
   CU(cudaSetDevice(e->device));
-  return finish_sync(e);
+  return finish_all(e);
 }
 
 int drs_infer_staged(drs_engine* e, int batch_id, int batch_size, float* out, drs_timing* tm) {
   CHECK_ARG(e, "engine is NULL");
   const auto t0 = std::chrono::steady_clock::now();
   CU(cudaSetDevice(e->device));
-  CU(cudaEventRecord(e->ev[1], e->stream));
-  TRY(drs_enqueue_staged(e, batch_id, batch_size));
-  CU(cudaEventRecord(e->ev[2], e->stream));
-  if (out)
-    CU(cudaMemcpyAsync(out, e->out, (size_t)batch_size * e->out_dim * sizeof(float),
-                       cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaEventRecord(e->ev[3], e->stream));
-  TRY(finish_sync(e));
+  Lane& ln = pick_lane(e);
+  CU(cudaEventRecord(ln.ev[1], ln.stream));
+  TRY(enqueue_staged_on(e, ln, batch_id, batch_size));
+  CU(cudaEventRecord(ln.ev[2], ln.stream));
+  if (out && ln.last_rows > 0)
+    CU(cudaMemcpyAsync(out, ln.out, (size_t)ln.last_rows * e->out_dim * sizeof(float),
+                       cudaMemcpyDeviceToHost, ln.stream));
+  CU(cudaEventRecord(ln.ev[3], ln.stream));
+  TRY(finish_lane(e, ln));
   if (tm) {
     tm->h2d_ms = 0.f;
-    CU(cudaEventElapsedTime(&tm->gpu_ms, e->ev[1], e->ev[2]));
-    CU(cudaEventElapsedTime(&tm->d2h_ms, e->ev[2], e->ev[3]));
+    CU(cudaEventElapsedTime(&tm->gpu_ms, ln.ev[1], ln.ev[2]));
+    CU(cudaEventElapsedTime(&tm->d2h_ms, ln.ev[2], ln.ev[3]));
     tm->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0)
                        .count();
   }
+  return DRS_OK;
+}
+
+static int enqueue_host_on(drs_engine* e, Lane& ln, const float* dense, const void* const* idx,
+                           int idx_is_i64, const int32_t* const* lengths, int batch_size,
+                           float* out_pinned) {
+  const int64_t cap = (int64_t)e->spec.max_batch * e->world;
+  CHECK_ARG(batch_size >= 1 && batch_size <= cap && batch_size <= ln.slot.n,
+            "batch_size %d out of range [1,%lld]", batch_size, (long long)cap);
+  CU(cudaSetDevice(e->device));
+  TRY(check_ready(e));
+  std::vector<int64_t> n_idx;
+  CU(cudaEventRecord(ln.ev[0], ln.stream));
+  TRY(upload_inputs(e, ln.slot, ln.stream, dense, idx, idx_is_i64, lengths, batch_size, &n_idx));
+  CU(cudaEventRecord(ln.ev[1], ln.stream));
+  TRY(launch_scan(e, ln.stream, ln.slot, batch_size, ln.d_err));
+  TRY(enqueue_graph(e, ln, ln.slot, batch_size));
+  CU(cudaEventRecord(ln.ev[2], ln.stream));
+  if (out_pinned && ln.last_rows > 0)
+    CU(cudaMemcpyAsync(out_pinned, ln.out, (size_t)ln.last_rows * e->out_dim * sizeof(float),
+                       cudaMemcpyDeviceToHost, ln.stream));
+  CU(cudaEventRecord(ln.ev[3], ln.stream));
   return DRS_OK;
 }
 
 int drs_enqueue_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
                      const int32_t* const* lengths, int batch_size, float* out_pinned) {
   CHECK_ARG(e, "engine is NULL");
-  CHECK_ARG(batch_size >= 1 && batch_size <= e->spec.max_batch,
-            "batch_size %d out of range [1,%d]", batch_size, e->spec.max_batch);
-  CU(cudaSetDevice(e->device));
-  TRY(check_ready(e));
-  std::vector<int64_t> n_idx;
-  CU(cudaEventRecord(e->ev[0], e->stream));
-  TRY(upload_inputs(e, e->slot, dense, idx, idx_is_i64, lengths, batch_size, &n_idx));
-  CU(cudaEventRecord(e->ev[1], e->stream));
-  TRY(launch_scan(e, e->slot, batch_size));
-  TRY(enqueue_graph(e, e->slot, batch_size));
-  CU(cudaEventRecord(e->ev[2], e->stream));
-  if (out_pinned)
-    CU(cudaMemcpyAsync(out_pinned, e->out, (size_t)batch_size * e->out_dim * sizeof(float),
-                       cudaMemcpyDeviceToHost, e->stream));
-  CU(cudaEventRecord(e->ev[3], e->stream));
-  return DRS_OK;
+  Lane& ln = pick_lane(e);
+  // the lane's input slot is reused: the previous query on this lane must have been consumed
+  CU(cudaStreamSynchronize(ln.stream));
+  return enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out_pinned);
 }
 
 int drs_infer(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
               const int32_t* const* lengths, int batch_size, float* out, drs_timing* tm) {
+  CHECK_ARG(e, "engine is NULL");
   const auto t0 = std::chrono::steady_clock::now();
-  TRY(drs_enqueue_host(e, dense, idx, idx_is_i64, lengths, batch_size, out));
-  TRY(finish_sync(e));
+  Lane& ln = pick_lane(e);
+  CU(cudaStreamSynchronize(ln.stream));
+  TRY(enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out));
+  TRY(finish_lane(e, ln));
   if (tm) {
-    CU(cudaEventElapsedTime(&tm->h2d_ms, e->ev[0], e->ev[1]));
-    CU(cudaEventElapsedTime(&tm->gpu_ms, e->ev[1], e->ev[2]));
-    CU(cudaEventElapsedTime(&tm->d2h_ms, e->ev[2], e->ev[3]));
+    CU(cudaEventElapsedTime(&tm->h2d_ms, ln.ev[0], ln.ev[1]));
+    CU(cudaEventElapsedTime(&tm->gpu_ms, ln.ev[1], ln.ev[2]));
+    CU(cudaEventElapsedTime(&tm->d2h_ms, ln.ev[2], ln.ev[3]));
     tm->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0)
                        .count();
   }
   return DRS_OK;
 }
 
+// Stopwatch spanning all lanes: t0 is after everything enqueued so far and before anything
+// enqueued later; t1 is after everything enqueued before the stop.
 int drs_timer_start(drs_engine* e) {
   CHECK_ARG(e, "engine is NULL");
   CU(cudaSetDevice(e->device));
-  CU(cudaEventRecord(e->ev_timer[0], e->stream));
+  for (int i = 1; i < e->n_lanes; ++i) {
+    CU(cudaEventRecord(e->lanes[i].tail, e->lanes[i].stream));
+    CU(cudaStreamWaitEvent(s0(e), e->lanes[i].tail, 0));
+  }
+  CU(cudaEventRecord(e->ev_timer[0], s0(e)));
+  for (int i = 1; i < e->n_lanes; ++i) CU(cudaStreamWaitEvent(e->lanes[i].stream, e->ev_timer[0], 0));
   return DRS_OK;
 }
 
 int drs_timer_stop(drs_engine* e, float* elapsed_ms) {
   CHECK_ARG(e && elapsed_ms, "NULL argument");
   CU(cudaSetDevice(e->device));
-  CU(cudaEventRecord(e->ev_timer[1], e->stream));
+  for (int i = 1; i < e->n_lanes; ++i) {
+    CU(cudaEventRecord(e->lanes[i].tail, e->lanes[i].stream));
+    CU(cudaStreamWaitEvent(s0(e), e->lanes[i].tail, 0));
+  }
+  CU(cudaEventRecord(e->ev_timer[1], s0(e)));
   CU(cudaEventSynchronize(e->ev_timer[1]));
   CU(cudaEventElapsedTime(elapsed_ms, e->ev_timer[0], e->ev_timer[1]));
   return DRS_OK;
@@ -940,6 +1176,8 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
   if (!e->table_loaded[table]) return fail(DRS_ERR_STATE, "table %d not loaded", table);
   if (n_segments == 0) return DRS_OK;
   CU(cudaSetDevice(e->device));
+  Lane& ln = e->lanes[0];
+  cudaStream_t st = ln.stream;
   const int D = e->D;
   int32_t *d_idx = nullptr, *d_len = nullptr, *d_off = nullptr;
   int64_t* d_idx64 = nullptr;
@@ -952,7 +1190,7 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
   };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(DRS_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUC(cudaMalloc(&d_idx, ((size_t)n_idx + 8) * sizeof(int32_t)));
-  CUC(cudaMemsetAsync(d_idx, 0, ((size_t)n_idx + 8) * sizeof(int32_t), e->stream));
+  CUC(cudaMemsetAsync(d_idx, 0, ((size_t)n_idx + 8) * sizeof(int32_t), st));
   CUC(cudaMalloc(&d_len, (size_t)n_segments * sizeof(int32_t)));
   CUC(cudaMalloc(&d_off, ((size_t)n_segments + 1) * sizeof(int32_t)));
   CUC(cudaMalloc(&d_out, (size_t)n_segments * D * sizeof(float)));
@@ -962,24 +1200,24 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
     if (idx_is_i64) {
       CUC(cudaMalloc(&d_idx64, (size_t)n_idx * sizeof(int64_t)));
       CUC(cudaMemcpyAsync(d_idx64, idx, (size_t)n_idx * sizeof(int64_t), cudaMemcpyHostToDevice,
-                          e->stream));
-      k_cast_i64_i32<<<ew_grid(n_idx), 256, 0, e->stream>>>(d_idx64, d_idx, n_idx);
+                          st));
+      k_cast_i64_i32<<<ew_grid(n_idx), 256, 0, st>>>(d_idx64, d_idx, n_idx);
       e->launches += 1;
     } else {
       CUC(cudaMemcpyAsync(d_idx, idx, (size_t)n_idx * sizeof(int32_t), cudaMemcpyHostToDevice,
-                          e->stream));
+                          st));
     }
   }
   CUC(cudaMemcpyAsync(d_len, lengths, (size_t)n_segments * sizeof(int32_t),
-                      cudaMemcpyHostToDevice, e->stream));
+                      cudaMemcpyHostToDevice, st));
   SlsTableDesc hd{};
   hd.rows = e->tables[table]; hd.idx = d_idx; hd.off = d_off; hd.n_rows = e->table_rows[table];
   hd.dst_col = 0;
   ScanTableDesc hs{};
   hs.lengths = d_len; hs.off = d_off; hs.n_idx = n_idx;
-  CUC(cudaMemcpyAsync(d_desc, &hd, sizeof(hd), cudaMemcpyHostToDevice, e->stream));
-  CUC(cudaMemcpyAsync(d_scan, &hs, sizeof(hs), cudaMemcpyHostToDevice, e->stream));
-  k_lengths_to_offsets<<<1, kScanThreads, 0, e->stream>>>(d_scan, n_segments, e->d_err);
+  CUC(cudaMemcpyAsync(d_desc, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
+  CUC(cudaMemcpyAsync(d_scan, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+  k_lengths_to_offsets<<<1, kScanThreads, 0, st>>>(d_scan, n_segments, ln.d_err);
   e->launches += 1;
   {
     int lpr, SB, cap; size_t smem;
@@ -989,14 +1227,14 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
     p.tables = d_desc; p.T = 1; p.B = n_segments; p.D = D;
     p.out = d_out; p.ld_out = D; p.SB = SB; p.idx_cap = cap;
     p.vec_store = (D % 4 == 0) ? 1 : 0;
-    p.err_flag = e->d_err;
-    int rc = launch_gather_lpr<false>(e, p, lpr, ceil_div(n_segments, SB), smem);
+    p.err_flag = ln.d_err;
+    int rc = launch_gather_lpr<false>(e, st, p, lpr, ceil_div(n_segments, SB), smem);
     if (rc != DRS_OK) { cleanup(); return rc; }
   }
   CUC(cudaMemcpyAsync(out, d_out, (size_t)n_segments * D * sizeof(float), cudaMemcpyDeviceToHost,
-                      e->stream));
-  CUC(cudaMemcpyAsync(e->h_err, e->d_err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  int rc = finish_sync(e);
+                      st));
+  CUC(cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int rc = finish_lane(e, ln);
   cleanup();
   return rc;
 #undef CUC
@@ -1005,52 +1243,54 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
 int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap, int* rows,
                     int* cols) {
   CHECK_ARG(e && dst && rows && cols, "NULL argument");
-  CHECK_ARG(e->last_inputs && e->last_B > 0, "no query has been served yet");
+  Lane& ln = e->lanes[e->last_lane];
+  CHECK_ARG(ln.last_inputs && ln.last_B > 0, "no query has been served yet");
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
-  const int B = e->last_B, D = e->D, T = e->T;
+  TRY(sync_all(e));
+  const int B = ln.last_rows, D = e->D, T = e->T;   // rows held by this rank
   const float* src = nullptr;
   int64_t ld = 0;
   int r = B, c = 0;
   switch (stage) {
     case DRS_STAGE_POOLED:
       c = T * D;
-      if (e->P) { src = e->P; ld = (int64_t)T * D; }
-      else { src = e->R + gather_dst_col(e, 0); ld = e->ld_R; }
+      if (ln.P) { src = ln.P; ld = (int64_t)T * D; }
+      else { src = ln.R + gather_dst_col(e, 0); ld = e->ld_R; }
       break;
     case DRS_STAGE_BOT: {
-      if (e->spec.model_type == DRS_MODEL_DIN) { src = e->R + D; ld = e->ld_R; c = D; break; }
+      if (e->spec.model_type == DRS_MODEL_DIN) { src = ln.R + D; ld = e->ld_R; c = D; break; }
       CHECK_ARG(e->spec.model_type == DRS_MODEL_DLRM, "model has no bottom MLP");
       CHECK_ARG(layer >= 0 && layer < (int)e->bot.layers.size(), "bottom layer out of range");
       const Layer& l = e->bot.layers[layer];
       c = l.out;
       if (layer == (int)e->bot.layers.size() - 1) {
-        if (e->dense_out) { src = e->dense_out; ld = D; } else { src = e->R; ld = e->ld_R; }
-      } else { src = l.y; ld = l.out; }
+        if (ln.dense_out) { src = ln.dense_out; ld = D; } else { src = ln.R; ld = e->ld_R; }
+      } else { src = ln.ybot[layer]; ld = l.out; }
       break;
     }
     case DRS_STAGE_INTERACT:
       if (e->spec.model_type == DRS_MODEL_NCF) {
-        src = e->F; c = D + e->top.layers.back().out; ld = c;
-      } else { src = e->R; c = e->ld_R; ld = e->ld_R; }
+        src = ln.F; c = D + e->top.layers.back().out; ld = c;
+      } else { src = ln.R; c = e->ld_R; ld = e->ld_R; }
       break;
     case DRS_STAGE_TOP: {
       CHECK_ARG(layer >= 0 && layer < (int)e->top.layers.size(), "top layer out of range");
       const Layer& l = e->top.layers[layer];
       c = l.out;
       if (e->spec.model_type == DRS_MODEL_NCF && layer == (int)e->top.layers.size() - 1) {
-        src = e->F + D; ld = D + l.out;
-      } else { src = l.y; ld = l.out; }
+        src = ln.F + D; ld = D + l.out;
+      } else { src = ln.ytop[layer]; ld = l.out; }
       break;
     }
     case DRS_STAGE_OUT:
-      src = e->out; c = e->out_dim; ld = c;
+      src = ln.out; c = e->out_dim; ld = c;
       break;
     case DRS_STAGE_OFFSETS: {
-      r = T; c = B + 1;
+      r = T; c = ln.last_B + 1;
       CHECK_ARG((int64_t)r * c <= cap, "capacity too small: need %lld floats", (long long)r * c);
-      CU(cudaMemcpy2D(dst, (size_t)c * 4, e->last_inputs->off, (size_t)(e->last_inputs->n + 1) * 4,
-                      (size_t)c * 4, r, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy2D(dst, (size_t)c * 4, ln.last_inputs->off,
+                      (size_t)(ln.last_inputs->n + 1) * 4, (size_t)c * 4, r,
+                      cudaMemcpyDeviceToHost));
       *rows = r; *cols = c;
       return DRS_OK;
     }
@@ -1058,8 +1298,9 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
       return fail(DRS_ERR_INVALID, "unknown stage %d", stage);
   }
   CHECK_ARG((int64_t)r * c <= cap, "capacity too small: need %lld floats", (long long)r * c);
-  CU(cudaMemcpy2D(dst, (size_t)c * 4, src, (size_t)ld * 4, (size_t)c * 4, r,
-                  cudaMemcpyDeviceToHost));
+  if (r > 0)
+    CU(cudaMemcpy2D(dst, (size_t)c * 4, src, (size_t)ld * 4, (size_t)c * 4, r,
+                    cudaMemcpyDeviceToHost));
   *rows = r; *cols = c;
   return DRS_OK;
 }
@@ -1094,7 +1335,7 @@ int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms
   CHECK_ARG(e && n_steps && pre_ms && gather_ms && post_ms, "NULL argument");
   CU(cudaSetDevice(e->device));
   e->prof_on = false;
-  CU(cudaStreamSynchronize(e->stream));
+  TRY(sync_all(e));
   double a = 0, b = 0, c = 0;
   for (int i = 0; i < e->prof_n; ++i) {
     float t;
@@ -1109,13 +1350,48 @@ int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms
 
 int drs_shard_export(drs_engine* e, void* blob_out) {
   CHECK_ARG(e && blob_out, "NULL argument");
-  return fail(DRS_ERR_COMM, "table-sharded exchange is not built in this version");
+  CU(cudaSetDevice(e->device));
+  ShardBlob b{};
+  b.magic = 0x44525331u;   // "DRS1"
+  b.n_lanes = e->n_lanes;
+  b.device = e->device;
+  b.slab_bytes = e->slab_bytes;
+  b.flags_off = e->flags_off;
+  for (int i = 0; i < kMaxLanes; ++i) b.lane_G_off[i] = e->lane_G_off[i];
+  CU(cudaIpcGetMemHandle(&b.handle, e->slab));
+  std::memset(blob_out, 0, DRS_SHARD_BLOB_BYTES);
+  std::memcpy(blob_out, &b, sizeof(b));
+  return DRS_OK;
 }
 
 int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs) {
   CHECK_ARG(e && all_blobs, "NULL argument");
-  (void)rank; (void)world;
-  return fail(DRS_ERR_COMM, "table-sharded exchange is not built in this version");
+  CHECK_ARG(world >= 1 && world <= kMaxShardRanks && rank >= 0 && rank < world,
+            "rank %d / world %d out of range (max %d ranks)", rank, world, kMaxShardRanks);
+  CHECK_ARG(!(e->dot), "table-sharded mode does not support the fused dot interaction "
+                       "(it needs every table of a sample in one CTA); use replica mode");
+  CHECK_ARG(e->world == 1, "already connected");
+  CU(cudaSetDevice(e->device));
+  TRY(sync_all(e));
+  const unsigned char* blobs = static_cast<const unsigned char*>(all_blobs);
+  for (int q = 0; q < world; ++q) {
+    ShardBlob b;
+    std::memcpy(&b, blobs + (size_t)q * DRS_SHARD_BLOB_BYTES, sizeof(b));
+    if (b.magic != 0x44525331u || b.n_lanes != e->n_lanes || b.slab_bytes != e->slab_bytes ||
+        b.flags_off != e->flags_off)
+      return fail(DRS_ERR_COMM, "rank %d exported an incompatible exchange slab", q);
+    if (q == rank) { e->peer_slab[q] = e->slab; continue; }
+    void* p = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess)
+      return fail(DRS_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) -> %s", q, cudaGetErrorString(ce));
+    e->peer_slab[q] = static_cast<unsigned char*>(p);
+  }
+  e->rank = rank;
+  e->world = world;
+  e->owned.clear();
+  for (int t = 0; t < e->T; ++t) if (owns(e, t)) e->owned.push_back(t);
+  return rewrite_all_descs(e);
 }
 
 }  // extern "C"

@@ -29,6 +29,7 @@ namespace drs {
 
 constexpr int kSlsThreads = 256;
 constexpr int kSlsUnroll = 8;
+constexpr int kMaxShardRanks = 8;
 
 struct SlsTableDesc {
   const float* rows;      // [n_rows, D] table in HBM
@@ -53,6 +54,11 @@ struct SlsLaunch {
   int64_t ld_dense;
   int itself;             // arch_interaction_itself
   float* pooled_tap;      // optional [B, T*D] copy of pooled vectors (debug tap), or nullptr
+  // table-sharded multi-GPU (shard_S > 0): sample b belongs to rank b / shard_S and its pooled
+  // vector is stored straight into that rank's buffer (peer-mapped over NVLink) at local row
+  // b % shard_S — the all-to-all exchange is this kernel's epilogue.
+  int shard_S;
+  float* peer_out[kMaxShardRanks];
 };
 
 __host__ __device__ inline size_t sls_smem_bytes(int T, int SB, int idx_cap, int D, bool fuse_dot) {
@@ -198,7 +204,9 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
           *reinterpret_cast<float4*>(p.pooled_tap + b * ((int64_t)p.T * p.D) + (int64_t)t * p.D +
                                      lane * 4) = acc;
       } else {
-        float* o = p.out + b * p.ld_out + td.dst_col + lane * 4;
+        float* o = (p.shard_S > 0
+                        ? p.peer_out[b / p.shard_S] + (b % p.shard_S) * p.ld_out
+                        : p.out + b * p.ld_out) + td.dst_col + lane * 4;
         if (p.vec_store) {
           *reinterpret_cast<float4*>(o) = acc;
         } else {
@@ -225,6 +233,8 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
         if (FUSE_DOT) {
           spool[(size_t)(lb * (p.T + 1) + 1 + t) * (p.D + 1) + c] = acc;
           if (p.pooled_tap) p.pooled_tap[b * ((int64_t)p.T * p.D) + (int64_t)t * p.D + c] = acc;
+        } else if (p.shard_S > 0) {
+          p.peer_out[b / p.shard_S][(b % p.shard_S) * p.ld_out + td.dst_col + c] = acc;
         } else {
           p.out[b * p.ld_out + td.dst_col + c] = acc;
         }

@@ -29,7 +29,8 @@ def _ptr_array(arrays):
 
 
 class AccelEngine(object):
-    def __init__(self, args=None, spec=None, device=0, max_batch=None, precision=None):
+    def __init__(self, args=None, spec=None, device=0, max_batch=None, precision=None,
+                 lanes=0, max_lookups_per_table=None):
         self.lib = _lib.load()
         self.spec = spec if spec is not None else ModelSpec(args)
         s = self.spec
@@ -54,8 +55,9 @@ class AccelEngine(object):
         cs.interaction_op = _lib.INTERACT_DOT if s.interaction_op == "dot" else _lib.INTERACT_CAT
         cs.interaction_itself = int(s.interaction_itself)
         cs.max_batch = self.max_batch
-        cs.max_lookups_per_table = self.max_batch * max(1, s.L)
+        cs.max_lookups_per_table = int(max_lookups_per_table or self.max_batch * max(1, s.L))
         cs.precision = _lib.PRECISIONS[precision]
+        cs.n_lanes = int(lanes)
         self._handle = C.c_void_p()
         _lib.check(self.lib.drs_create(C.byref(cs), int(device), C.byref(self._handle)))
         self.out_dim = s.out_dim
@@ -228,6 +230,21 @@ class AccelEngine(object):
         _lib.check(self.lib.drs_profile_end(self._handle, C.byref(n), C.byref(a), C.byref(b),
                                             C.byref(c)))
         return n.value, a.value, b.value, c.value
+
+    # multi-GPU, one process per GPU ------------------------------------------
+    def shard_export(self):
+        """64-byte CUDA-IPC handle + layout of this rank's exchange slab."""
+        blob = (C.c_ubyte * _lib.SHARD_BLOB_BYTES)()
+        _lib.check(self.lib.drs_shard_export(self._handle, blob))
+        return bytes(blob)
+
+    def shard_connect(self, rank, world, blobs):
+        """``blobs``: the exported blob of every rank, in rank order."""
+        assert len(blobs) == world
+        buf = b"".join(blobs)
+        arr = (C.c_ubyte * len(buf)).from_buffer_copy(buf)
+        _lib.check(self.lib.drs_shard_connect(self._handle, int(rank), int(world), arr))
+        self.rank, self.world = int(rank), int(world)
 
     def launch_count(self):
         n = C.c_int64()

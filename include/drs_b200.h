@@ -87,7 +87,7 @@ typedef struct {
   int32_t max_batch;             /* largest query (samples)                                  */
   int32_t max_lookups_per_table; /* largest sum(lengths) of one table in one query           */
   int32_t precision;             /* DRS_PREC_*                                               */
-  int32_t reserved;
+  int32_t n_lanes;               /* concurrent query lanes (stream + activation set); 0 = default 2 */
 } drs_spec;
 
 /* per-call timing, milliseconds */
