@@ -54,6 +54,9 @@ def parse_args():
     p.add_argument("--precision", type=str, default="tf32x3",
                    help="MLP arithmetic: fp32 (FFMA) | tf32x3 (tcgen05, fp32-class) | tf32")
     p.add_argument("--lanes", type=int, default=2)
+    p.add_argument("--shard", type=str, default="replica", choices=["replica", "table"],
+                   help="N>1: replica (every rank all tables, own queries) | table (table-wise "
+                        "sharding, pooled vectors exchanged by K1's peer stores over NVLink)")
     p.add_argument("--interaction", type=str, default=None, help="override: cat | dot")
     p.add_argument("--cpu_seconds", type=float, default=10.0)
     p.add_argument("--cpu_sample", type=int, default=4096)
@@ -75,12 +78,14 @@ def model_args(opts, batch, num_batches):
     return a
 
 
-def synth_tables(spec, seed):
+def synth_tables(spec, seed, only=None):
     """Random-init tables of the reference's distribution U(+-sqrt(1/n)), drawn in
     float32 with a fast generator (bench only; the engine's drop-in path uses the
     reference's exact legacy-RNG draws, deeprecsys_b200/spec.py)."""
-    rng = np.random.default_rng(seed)
     for t, rows in enumerate(spec.table_rows):
+        if only is not None and t not in only:
+            continue
+        rng = np.random.default_rng([seed, t])
         W = rng.random((rows, spec.D), dtype=np.float32)
         bound = np.float32(np.sqrt(1.0 / rows))
         W *= 2 * bound
@@ -220,14 +225,23 @@ def run_b200(opts):
     from deeprecsys_b200.engine import AccelEngine, pinned_empty
     from deeprecsys_b200.spec import ModelSpec
 
-    B, nb = int(opts.batch), int(opts.staged_batches)
-    a = model_args(opts, B, nb)
+    from deeprecsys_b200 import shard as shardlib
+
+    B, nb = int(opts.batch), int(opts.staged_batches)        # B = samples per GPU per step
+    sharded = (world > 1 and opts.shard == "table")
+    GB = B * world if sharded else B                           # samples in one enqueued query
+    a = model_args(opts, GB, nb)
     spec = ModelSpec(a)
     eng = AccelEngine(args=a, device=local, max_batch=B, precision=opts.precision,
-                      lanes=opts.lanes)
+                      lanes=opts.lanes, max_lookups_per_table=GB * max(1, spec.L))
+    if sharded:
+        shardlib.connect(eng, dist)
     keep_host = (rank == 0 and world == 1 and not opts.no_cpu_baseline)
     host_tables = []
-    for t, W in synth_tables(spec, opts.seed + 1000 * rank):
+    only = set(shardlib.owned_tables(spec.T, rank, world)) if sharded else None
+    # replica: every rank has its own table contents and queries; table: one global model
+    tseed = opts.seed if sharded else opts.seed + 1000 * rank
+    for t, W in synth_tables(spec, tseed, only):
         eng.load_table(t, W)
         if keep_host:
             host_tables.append(W)
@@ -235,7 +249,7 @@ def run_b200(opts):
     for (mlp_id, layer), (W, b) in fcs.items():
         eng.load_fc(mlp_id, layer, W, b)
 
-    np.random.seed(opts.seed + rank)
+    np.random.seed(opts.seed + (0 if sharded else rank))
     _, lX, lS_l, lS_i = DLRMDataGenerator(a).generate_input_data()
     for j in range(nb):
         eng.stage_batch(j, lX[j] if spec.m_den > 0 else None,
@@ -255,7 +269,7 @@ def run_b200(opts):
 
     # ---------------- value: inputs resident in HBM, device-timed
     for i in range(max(3, opts.warmup)):
-        eng.enqueue_staged(i % nb, B)
+        eng.enqueue_staged(i % nb, GB)
     eng.sync()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local)
@@ -265,7 +279,7 @@ def run_b200(opts):
     eng.profile_begin(opts.steps)
     eng.timer_start()
     for i in range(opts.steps):
-        eng.enqueue_staged(i % nb, B)
+        eng.enqueue_staged(i % nb, GB)
     ms_total = eng.timer_stop()
     eng.sync()
     barrier()
@@ -280,7 +294,11 @@ def run_b200(opts):
     peak, peak_src = load_peaks()
     bytes_per_sample = spec.gather_bytes_per_sample(fused=True)
     gather_ms_avg = gather_ms / max(1, n_prof)
-    achieved = bytes_per_sample * B / (gather_ms_avg * 1e-3) / 1e9 if gather_ms_avg > 0 else 0.0
+    # per launch: this rank's tables x the query's samples (table mode: T/world tables x B*world
+    # samples = the same bytes as replica mode's T tables x B samples when T % world == 0)
+    own_frac = (len(only) / float(spec.T)) if sharded else 1.0
+    bytes_per_launch = bytes_per_sample * GB * own_frac
+    achieved = bytes_per_launch / (gather_ms_avg * 1e-3) / 1e9 if gather_ms_avg > 0 else 0.0
     roofline = {
         "kernel": "k_sls_gather (multi-table SparseLengthsSum + cat layout)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -294,7 +312,7 @@ def run_b200(opts):
 
     # ---------------- e2e: C-ABI with pinned HOST buffers, H2D + D2H inside
     e2e, latency = None, None
-    if not opts.no_e2e:
+    if not opts.no_e2e and not sharded:
         T, L = spec.T, spec.L
         h_idx, _k1 = pinned_empty((T, B * L), np.int32)
         h_len, _k2 = pinned_empty((T, B), np.int32)
@@ -345,7 +363,7 @@ def run_b200(opts):
 
     # ---------------- batch-size sweep (staged path), reference sweep shape 4^0..4^5 + larger
     sweep = None
-    if not opts.no_sweep and rank == 0:
+    if not opts.no_sweep and rank == 0 and not sharded:
         sweep = {}
         for bs in [1, 4, 16, 64, 256, 1024, 4096, 16384, 65536]:
             if bs > B:
@@ -392,7 +410,9 @@ def run_b200(opts):
                                    "staged in HBM" % (opts.config, spec.interaction_op, spec.T,
                                                      spec.table_rows[0], spec.D, spec.L, B,
                                                      max(1, B // 1024)),
-                       "global_batch": B * world, "parallelism": "replica x%d" % world,
+                       "global_batch": B * world,
+                       "parallelism": ("table-sharded x%d (K1 peer stores over NVLink)" % world
+                                       if sharded else "replica x%d" % world),
                        "l2_policy": "inputs larger than L2 (4.1 GB tables, uniform ids; "
                                     "%d staged batches cycled)" % nb,
                        "mlp_precision": opts.precision, "lanes": opts.lanes},
@@ -410,9 +430,32 @@ def run_b200(opts):
 
 def main():
     opts = parse_args()
-    if opts.impl == "reference":
-        return run_reference(opts)
-    return run_b200(opts)
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version
+    # banner) goes to stderr while the benchmark runs.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    import builtins
+    real_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            real_print(*a, **k)
+    builtins.print = capture
+    try:
+        rc = run_reference(opts) if opts.impl == "reference" else run_b200(opts)
+    finally:
+        builtins.print = real_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in lines:
+        real_print(line)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":

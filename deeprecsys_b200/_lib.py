@@ -75,6 +75,7 @@ _SIGNATURES = {
                                   C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "drs_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "drs_hbm_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "drs_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "drs_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "drs_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -88,7 +89,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB_PATH
+    # DRS_LIB_PATH: tuning experiments load an alternative build of the same library
+    return os.environ.get("DRS_LIB_PATH") or _build.LIB_PATH
 
 
 def load():

@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "interact.cuh"
 #include "mlp_ffma.cuh"
+#include "mlp_chain.cuh"
 #include "mlp_tc.cuh"
 #include "shard.cuh"
 #include "sls_gather.cuh"
@@ -157,9 +158,16 @@ struct drs_engine {
   int64_t launches = 0;
   int64_t hbm_bytes = 0;
 
+  // options (drs_set_option)
+  int gather_ctas_per_sm = 4; // > 0: persistent gather with that many CTAs per SM; 0: one CTA per tile
+  int n_sm = 148;
+  bool mlp_chain = true;      // fuse whole MLP stacks into one tcgen05 kernel when shapes allow
+  bool tap_hidden = false;    // chain mode: also store hidden activations for drs_fetch_stage
+
   // gather launch geometry
   int lpr = 0, SB = 1, idx_cap = 0;
   size_t sls_smem = 0;
+  bool table_major = false;
 
   // exchange slab: gather-output buffers of all lanes + flag arrays (one IPC handle)
   unsigned char* slab = nullptr;
@@ -338,15 +346,45 @@ int launch_fc(drs_engine* e, Lane& ln, const Layer& l, const float* X, int64_t l
 int run_mlp(drs_engine* e, Lane& ln, Mlp& m, std::vector<float*>& ys, const float* X, int64_t ldx,
             int64_t x_rows_total, int M, float* last_y = nullptr, int64_t last_ldy = 0) {
   const int nl = (int)m.layers.size();
+  if (M <= 0 || nl == 0) return DRS_OK;
   const float* in = X;
   int64_t ld_in = ldx, bs_in = 0, rows_in = x_rows_total;
-  for (int i = 0; i < nl; ++i) {
+  int i = 0;
+  while (i < nl) {
+    // try to fuse layers [i, i + g) into one tcgen05 chain kernel
+    if (e->mlp_chain && e->spec.precision != DRS_PREC_FP32 && m.layers[i].n_units == 1) {
+      ChainLayerHost hl[kChainMaxLayers];
+      int g = 0;
+      while (g < kChainMaxLayers && i + g < nl) {
+        const Layer& l = m.layers[i + g];
+        if (!l.Wsplit || l.n_units != 1 || l.out > 256 || l.in % 4 != 0) break;
+        hl[g].Wsplit = l.Wsplit; hl[g].bias = l.b; hl[g].N = l.out; hl[g].K = l.in; hl[g].act = l.act;
+        hl[g].tap = e->tap_hidden ? ys[i + g] : nullptr;
+        hl[g].ld_tap = l.out;
+        ++g;
+      }
+      if (g >= 2 && chain_supported(hl, g, ld_in, in)) {
+        const int lastl = i + g - 1;
+        float* y = ys[lastl];
+        int64_t ldy = m.layers[lastl].out;
+        if (lastl == nl - 1 && last_y) { y = last_y; ldy = last_ldy; }
+        int rc = chain_launch(in, ld_in, rows_in, hl, g, y, ldy, M,
+                              e->spec.precision == DRS_PREC_TF32X3, ln.stream);
+        if (rc != 0) return fail(DRS_ERR_CUDA, "MLP chain launch failed: %s",
+                                 cudaGetErrorString((cudaError_t)rc));
+        e->launches += 1;
+        in = y; ld_in = ldy; bs_in = 0; rows_in = e->spec.max_batch;
+        i += g;
+        continue;
+      }
+    }
     Layer& l = m.layers[i];
     float* y = ys[i];
     int64_t ldy = l.out, bsy = (int64_t)e->spec.max_batch * l.out;
     if (i == nl - 1 && last_y) { y = last_y; ldy = last_ldy; bsy = 0; }
     TRY(launch_fc(e, ln, l, in, ld_in, bs_in, rows_in, y, ldy, bsy, M));
     in = y; ld_in = ldy; bs_in = bsy; rows_in = e->spec.max_batch;
+    ++i;
   }
   return DRS_OK;
 }
@@ -365,6 +403,33 @@ int launch_gather_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid
   return DRS_OK;
 }
 
+template <int LPR>
+int launch_gather_persist_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid,
+                            size_t smem) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_sls_gather_persist<LPR>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  k_sls_gather_persist<LPR><<<grid, kSlsThreads, smem, st>>>(p);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return DRS_OK;
+}
+
+int launch_gather_persist(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
+                          size_t smem) {
+  switch (lpr) {
+    case 1:  return launch_gather_persist_t<1>(e, st, p, grid, smem);
+    case 2:  return launch_gather_persist_t<2>(e, st, p, grid, smem);
+    case 4:  return launch_gather_persist_t<4>(e, st, p, grid, smem);
+    case 8:  return launch_gather_persist_t<8>(e, st, p, grid, smem);
+    case 16: return launch_gather_persist_t<16>(e, st, p, grid, smem);
+    default: return launch_gather_persist_t<32>(e, st, p, grid, smem);
+  }
+}
+
 template <bool DOT>
 int launch_gather_lpr(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
                       size_t smem) {
@@ -379,8 +444,10 @@ int launch_gather_lpr(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lp
   }
 }
 
+// table_major: a CTA tile = SB samples of ONE table (see SlsLaunch::tiles_per_table)
 void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_out,
-                 int* idx_cap_out, size_t* smem_out) {
+                 int* idx_cap_out, size_t* smem_out, bool table_major = false) {
+  if (table_major) T = 1;
   int lpr = 0;
   if (D % 4 == 0) {
     const int q = D / 4;
@@ -418,7 +485,20 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
       p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_G_off[li]);
   }
   if (p.T == 0) return DRS_OK;
-  const int grid = ceil_div(B, e->SB);
+  int grid = ceil_div(B, e->SB);
+  // persistent path: vectorised rows, no dot fusion, offsets fit the per-thread registers
+  if (e->gather_ctas_per_sm > 0 && !dot && !e->table_major && e->lpr > 0 &&
+      p.T * (e->SB + 1) <= kPersistOffRegs * kSlsThreads) {
+    const size_t smem = sls_persist_smem_bytes(p.T, e->SB, e->idx_cap);
+    if (smem <= 100 * 1024) {
+      const int cap = e->n_sm * e->gather_ctas_per_sm;
+      return launch_gather_persist(e, ln.stream, p, e->lpr, grid < cap ? grid : cap, smem);
+    }
+  }
+  if (e->table_major && !dot) {
+    p.tiles_per_table = grid;
+    grid *= p.T;
+  }
   if (dot) return launch_gather_lpr<true>(e, ln.stream, p, e->lpr, grid, e->sls_smem);
   return launch_gather_lpr<false>(e, ln.stream, p, e->lpr, grid, e->sls_smem);
 }
@@ -435,6 +515,15 @@ int ew_grid(int64_t n) {
   if (g > 148 * 8) g = 148 * 8;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// true when layer `layer` of `m` is an interior layer of a fused chain and is not being tapped
+bool chain_hides(const drs_engine* e, const Mlp& m, int layer) {
+  if (!e->mlp_chain || e->tap_hidden || e->spec.precision == DRS_PREC_FP32) return false;
+  const int nl = (int)m.layers.size();
+  if (layer == nl - 1) return false;
+  // conservative: any interior layer of a multi-layer single-unit MLP may be fused
+  return nl >= 2 && m.layers[layer].n_units == 1;
 }
 
 // ------------------------------------------------------------ sharded exchange
@@ -765,6 +854,12 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   drs_engine* e = new drs_engine();
   e->spec = *spec;
   e->device = device;
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->n_sm = prop.multiProcessorCount;
+    const char* g = getenv("DRS_GATHER_CTAS_PER_SM");
+    if (g) e->gather_ctas_per_sm = atoi(g);
+  }
   e->T = spec->n_tables;
   e->D = spec->emb_dim;
   e->n_lanes = spec->n_lanes > 0 ? spec->n_lanes : 2;
@@ -898,7 +993,14 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   e->table_loaded.assign(T, 0);
 
   const int64_t avg_len = ceil_div64(max_lk, maxB);
-  plan_gather(T, D, avg_len, dlrm_dot, &e->lpr, &e->SB, &e->idx_cap, &e->sls_smem);
+  {
+    // "sample" (default) | "table".  Table-major was measured slower on B200 (5.16 vs 5.54 TB/s
+    // at RMC1: concentrating the chip on one table's id band costs DRAM bank parallelism).
+    const char* ord = getenv("DRS_GATHER_ORDER");
+    e->table_major = !dlrm_dot && ord && std::strcmp(ord, "table") == 0;
+  }
+  plan_gather(T, D, avg_len, dlrm_dot, &e->lpr, &e->SB, &e->idx_cap, &e->sls_smem,
+              e->table_major);
 
   TRYB(rewrite_all_descs(e));
   TRYB(sync_all(e));
@@ -1265,7 +1367,11 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
       c = l.out;
       if (layer == (int)e->bot.layers.size() - 1) {
         if (ln.dense_out) { src = ln.dense_out; ld = D; } else { src = ln.R; ld = e->ld_R; }
-      } else { src = ln.ybot[layer]; ld = l.out; }
+      } else {
+        CHECK_ARG(!chain_hides(e, e->bot, layer), "hidden activations stay on-chip in MLP-chain "
+                  "mode: drs_set_option(e, \"tap_hidden\", 1) before serving to tap them");
+        src = ln.ybot[layer]; ld = l.out;
+      }
       break;
     }
     case DRS_STAGE_INTERACT:
@@ -1279,7 +1385,11 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
       c = l.out;
       if (e->spec.model_type == DRS_MODEL_NCF && layer == (int)e->top.layers.size() - 1) {
         src = ln.F + D; ld = D + l.out;
-      } else { src = ln.ytop[layer]; ld = l.out; }
+      } else {
+        CHECK_ARG(!chain_hides(e, e->top, layer), "hidden activations stay on-chip in MLP-chain "
+                  "mode: drs_set_option(e, \"tap_hidden\", 1) before serving to tap them");
+        src = ln.ytop[layer]; ld = l.out;
+      }
       break;
     }
     case DRS_STAGE_OUT:
@@ -1348,6 +1458,16 @@ int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms
   return DRS_OK;
 }
 
+int drs_set_option(drs_engine* e, const char* key, int64_t value) {
+  CHECK_ARG(e && key, "NULL argument");
+  const std::string k(key);
+  if (k == "mlp_chain") e->mlp_chain = value != 0;
+  else if (k == "gather_ctas_per_sm") e->gather_ctas_per_sm = (int)value;
+  else if (k == "tap_hidden") e->tap_hidden = value != 0;
+  else return fail(DRS_ERR_INVALID, "unknown option '%s'", key);
+  return DRS_OK;
+}
+
 int drs_shard_export(drs_engine* e, void* blob_out) {
   CHECK_ARG(e && blob_out, "NULL argument");
   CU(cudaSetDevice(e->device));
@@ -1391,6 +1511,13 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
   e->world = world;
   e->owned.clear();
   for (int t = 0; t < e->T; ++t) if (owns(e, t)) e->owned.push_back(t);
+  {  // tile geometry follows the number of tables this rank gathers
+    const int64_t max_lk =
+        e->spec.max_lookups_per_table > 0 ? e->spec.max_lookups_per_table : e->spec.max_batch;
+    const int64_t avg_len = ceil_div64(max_lk, (int64_t)e->spec.max_batch * world);
+    plan_gather((int)e->owned.size() > 0 ? (int)e->owned.size() : 1, e->D, avg_len, false, &e->lpr,
+                &e->SB, &e->idx_cap, &e->sls_smem, e->table_major);
+  }
   return rewrite_all_descs(e);
 }
 

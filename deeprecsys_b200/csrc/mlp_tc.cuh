@@ -32,7 +32,13 @@
 namespace drs {
 
 constexpr int kTcBM = 128;
-constexpr int kTcBK = 32;          // fp32 per k-chunk: 128 bytes = one SWIZZLE_128B row
+#ifndef DRS_TC_BK
+#define DRS_TC_BK 16
+#endif
+// fp32 per k-chunk.  32 -> 128-byte rows (SWIZZLE_128B); 16 -> 64-byte rows (SWIZZLE_64B), half the
+// stage footprint, so twice the pipeline depth in the same shared memory.
+constexpr int kTcBK = DRS_TC_BK;
+static_assert(kTcBK == 16 || kTcBK == 32, "k-chunk must be one 64-B or 128-B swizzle row");
 constexpr int kTcThreads = 192;
 constexpr int kTcUmmaK = 8;        // tf32: 32 bytes per MMA K-step
 
@@ -127,15 +133,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, SWIZZLE_128B operand tile (rows x 128 B, 8-row groups 1024 B apart):
-// start>>4 | LBO=1 (unused for swizzled K-major) | SBO=1024>>4 | version=1 | layout=SWIZZLE_128B(2)
+// K-major swizzled operand tile: rows of kTcBK*4 bytes, 8-row groups SBO bytes apart.
+// start>>4 | LBO=1 (unused for swizzled K-major) | SBO>>4 | version=1 | layout type
+// (SWIZZLE_128B = 2 with 1024-B groups, SWIZZLE_64B = 4 with 512-B groups)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  constexpr uint64_t kSbo = 8 * kTcBK * 4;
+  constexpr uint64_t kLayout = kTcBK == 32 ? 2 : 4;
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (kSbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= kLayout << 61;
   return d;
 }
 
@@ -149,7 +158,7 @@ __host__ __device__ constexpr int tc_stage_bytes(int bn) {
   return 2 * kTcBM * kTcBK * 4 + 2 * bn * kTcBK * 4;   // A_hi, A_lo, B_hi, B_lo
 }
 __host__ __device__ constexpr int tc_stages(int bn) {
-  return bn >= 256 ? 2 : (bn >= 128 ? 3 : 4);
+  return (192 * 1024) / tc_stage_bytes(bn) > 8 ? 8 : (192 * 1024) / tc_stage_bytes(bn);
 }
 __host__ __device__ constexpr int tc_smem_bytes(int bn) {
   return tc_stages(bn) * tc_stage_bytes(bn) + 1024 /*align*/ + 256 /*barriers*/;
@@ -250,7 +259,7 @@ k_fc_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtens
         float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(tiles + (size_t)s * STAGE_BYTES + A_BYTES);
 #pragma unroll
-        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {   // 128 threads x 16 B per pass
           const int i = j * 128 + t;
           float4 v = hi[i];
           float4 h, l;
@@ -344,7 +353,8 @@ inline bool tc_make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_
   cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kTcBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -27,8 +27,14 @@
 
 namespace drs {
 
-constexpr int kSlsThreads = 256;
-constexpr int kSlsUnroll = 8;
+#ifndef DRS_SLS_THREADS
+#define DRS_SLS_THREADS 256
+#endif
+#ifndef DRS_SLS_UNROLL
+#define DRS_SLS_UNROLL 8
+#endif
+constexpr int kSlsThreads = DRS_SLS_THREADS;
+constexpr int kSlsUnroll = DRS_SLS_UNROLL;
 constexpr int kMaxShardRanks = 8;
 
 struct SlsTableDesc {
@@ -59,6 +65,13 @@ struct SlsLaunch {
   // b % shard_S — the all-to-all exchange is this kernel's epilogue.
   int shard_S;
   float* peer_out[kMaxShardRanks];
+  // CTA order.  0: sample-major (a CTA owns SB samples x all T tables; required by FUSE_DOT).
+  // > 0: table-major — CTA b handles table b / tiles_per_table, samples tile b % tiles_per_table
+  // (SB samples of that one table).  CTAs are scheduled in index order, so the whole chip sweeps
+  // one table at a time; ids are sorted inside every sample (np.unique in the generator), so all
+  // resident segments walk the table in ascending order roughly in lockstep and concurrent row
+  // reads fall into a narrow band of the table (DRAM page locality, L2 hits on shared rows).
+  int tiles_per_table;
 };
 
 __host__ __device__ inline size_t sls_smem_bytes(int T, int SB, int idx_cap, int D, bool fuse_dot) {
@@ -125,42 +138,47 @@ __device__ __forceinline__ float4 sls_segment_vec4(const float* __restrict__ row
 template <int LPR, bool FUSE_DOT>
 __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int Tc = p.tiles_per_table > 0 ? 1 : p.T;   // tables per CTA tile
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   int32_t* sidx = reinterpret_cast<int32_t*>(smem_raw + 16);
-  int32_t* soff = sidx + (size_t)p.T * p.idx_cap;
+  int32_t* soff = sidx + (size_t)Tc * p.idx_cap;
   float* spool = nullptr;  // [SB][T+1][D+1] (dot only)
   if (FUSE_DOT) {
-    size_t o = 16 + ((size_t)p.T * p.idx_cap + (size_t)p.T * (p.SB + 1)) * sizeof(int32_t);
+    size_t o = 16 + ((size_t)Tc * p.idx_cap + (size_t)Tc * (p.SB + 1)) * sizeof(int32_t);
     o = (o + 15) & ~size_t(15);
     spool = reinterpret_cast<float*>(smem_raw + o);
   }
 
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * p.SB;
+  const bool tm = p.tiles_per_table > 0;
+  const int t_first = tm ? blockIdx.x / p.tiles_per_table : 0;
+  const int T = tm ? 1 : p.T;
+  const SlsTableDesc* __restrict__ tabs = p.tables + t_first;
+  const int b0 = (tm ? blockIdx.x - t_first * p.tiles_per_table : blockIdx.x) * p.SB;
   const int sbe = min(p.SB, p.B - b0);
   const int SB1 = p.SB + 1;
   const bool use_smem_idx = p.idx_cap > 0;
 
   // 1. offsets of the tile -> smem
-  for (int i = tid; i < p.T * SB1; i += kSlsThreads) {
+  for (int i = tid; i < T * SB1; i += kSlsThreads) {
     const int t = i / SB1, j = i - t * SB1;
-    soff[i] = (j <= sbe) ? __ldg(p.tables[t].off + b0 + j) : 0;
+    soff[i] = (j <= sbe) ? __ldg(tabs[t].off + b0 + j) : 0;
   }
   if (use_smem_idx && tid == 0) {
-    mbar_init(bar, (uint32_t)p.T);
+    mbar_init(bar, (uint32_t)T);
     mbar_fence_init();
   }
   __syncthreads();
 
   // 2. index spans of the tile -> smem by TMA bulk copies (one per table)
   if (use_smem_idx) {
-    for (int t = tid; t < p.T; t += kSlsThreads) {
+    for (int t = tid; t < T; t += kSlsThreads) {
       const int beg = soff[t * SB1], end = soff[t * SB1 + sbe];
       const int a0 = beg & ~3;
       const int n = (end - a0 + 3) & ~3;
       if (n > 0 && n <= p.idx_cap) {
         mbar_arrive_expect_tx(bar, (uint32_t)n * 4u);
-        tma_load_1d(sidx + (size_t)t * p.idx_cap, p.tables[t].idx + a0, (uint32_t)n * 4u, bar);
+        tma_load_1d(sidx + (size_t)t * p.idx_cap, tabs[t].idx + a0, (uint32_t)n * 4u, bar);
       } else {
         mbar_arrive(bar);
       }
@@ -176,14 +194,14 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
   if (use_smem_idx) mbar_wait(bar, 0);
 
   // 3. gather: lane groups walk segments
-  const int nseg = sbe * p.T;
+  const int nseg = sbe * T;
   if (LPR > 0) {
     constexpr int L = LPR > 0 ? LPR : 1;
     const int group = tid / L, lane = tid - group * L;
     constexpr int ngroups = kSlsThreads / L;
     for (int s = group; s < nseg; s += ngroups) {
       const int t = s / sbe, lb = s - t * sbe;
-      const SlsTableDesc td = p.tables[t];
+      const SlsTableDesc td = tabs[t];
       const int tile_beg = soff[t * SB1], tile_end = soff[t * SB1 + sbe];
       const int beg = soff[t * SB1 + lb], end = soff[t * SB1 + lb + 1];
       const int a0 = tile_beg & ~3;
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
     constexpr int nwarps = kSlsThreads / kWarp;
     for (int s = warp; s < nseg; s += nwarps) {
       const int t = s / sbe, lb = s - t * sbe;
-      const SlsTableDesc td = p.tables[t];
+      const SlsTableDesc td = tabs[t];
       const int beg = soff[t * SB1 + lb], end = soff[t * SB1 + lb + 1];
       const int64_t b = b0 + lb;
       for (int c = lane; c < p.D; c += kWarp) {
@@ -271,6 +289,138 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
     for (int w = tid; w < sbe * p.D; w += kSlsThreads) {
       const int lb = w / p.D, c = w - lb * p.D;
       p.out[(int64_t)(b0 + lb) * p.ld_out + c] = spool[(size_t)(lb * F) * Dp + c];
+    }
+  }
+}
+
+// Persistent variant of K1 (cat layout / plain pooling, vectorised rows only): a fixed number of
+// CTAs per SM loop over the sample tiles (tile = blockIdx.x + k * gridDim.x).  While tile k is
+// being gathered, the offsets of tile k+2 are in registers and the index spans of tile k+1 are
+// landing in the other half of the double-buffered shared memory (TMA bulk copies on a second
+// mbarrier).  Because the CTAs never retire, their SM footprint is static, which leaves a fixed
+// share of registers / shared memory on every SM for the tensor-core MLP kernel of the
+// neighbouring lane to run *concurrently* with the gather (engine.cu lanes).
+constexpr int kPersistOffRegs = 2;     // offsets per thread kept in registers: T*(SB+1) <= 512
+
+__host__ __device__ inline size_t sls_persist_smem_bytes(int T, int SB, int idx_cap) {
+  size_t b = 32;                                              // two mbarriers (+pad)
+  b += 2 * (size_t)T * idx_cap * sizeof(int32_t);             // index spans, double-buffered
+  b += 2 * (size_t)T * (SB + 1) * sizeof(int32_t);            // offsets, double-buffered
+  return (b + 15) & ~size_t(15);
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLaunch p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);            // bar[0], bar[1]
+  int32_t* sidx0 = reinterpret_cast<int32_t*>(smem_raw + 32);
+  const size_t idx_words = (size_t)p.T * p.idx_cap;
+  const int SB1 = p.SB + 1;
+  const int noff = p.T * SB1;
+  int32_t* soff0 = sidx0 + 2 * idx_words;
+
+  const int tid = threadIdx.x;
+  const int T = p.T;
+  const SlsTableDesc* __restrict__ tabs = p.tables;
+  const int ntiles = (p.B + p.SB - 1) / p.SB;
+  const bool use_smem_idx = p.idx_cap > 0;
+  constexpr int L = LPR;
+  const int group = tid / L, lane = tid - group * L;
+  constexpr int ngroups = kSlsThreads / L;
+
+  // offsets of tile `tile` held by this thread (entries tid, tid + kSlsThreads)
+  auto load_offs = [&](int tile, int32_t* regs) {
+    const int b0 = tile * p.SB;
+    const int sbe = min(p.SB, p.B - b0);
+#pragma unroll
+    for (int k = 0; k < kPersistOffRegs; ++k) {
+      const int i = tid + k * kSlsThreads;
+      regs[k] = 0;
+      if (i < noff && tile < ntiles) {
+        const int t = i / SB1, j = i - t * SB1;
+        if (j <= sbe) regs[k] = __ldg(tabs[t].off + b0 + j);
+      }
+    }
+  };
+  auto store_offs = [&](int buf, const int32_t* regs) {
+#pragma unroll
+    for (int k = 0; k < kPersistOffRegs; ++k) {
+      const int i = tid + k * kSlsThreads;
+      if (i < noff) soff0[(size_t)buf * noff + i] = regs[k];
+    }
+  };
+  auto issue_spans = [&](int tile, int buf) {      // index spans of `tile` -> sidx[buf] by TMA
+    const int b0 = tile * p.SB;
+    const int sbe = min(p.SB, p.B - b0);
+    const int32_t* so = soff0 + (size_t)buf * noff;
+    for (int t = tid; t < T; t += kSlsThreads) {
+      const int beg = so[t * SB1], end = so[t * SB1 + sbe];
+      const int a0 = beg & ~3;
+      const int n = (end - a0 + 3) & ~3;
+      if (n > 0 && n <= p.idx_cap) {
+        mbar_arrive_expect_tx(&bar[buf], (uint32_t)n * 4u);
+        tma_load_1d(sidx0 + (size_t)buf * idx_words + (size_t)t * p.idx_cap, tabs[t].idx + a0,
+                    (uint32_t)n * 4u, &bar[buf]);
+      } else {
+        mbar_arrive(&bar[buf]);
+      }
+    }
+  };
+
+  int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  int32_t regs[kPersistOffRegs];
+  load_offs(tile, regs);
+  if (use_smem_idx && tid == 0) {
+    mbar_init(&bar[0], (uint32_t)T);
+    mbar_init(&bar[1], (uint32_t)T);
+    mbar_fence_init();
+  }
+  store_offs(0, regs);
+  load_offs(tile + gridDim.x, regs);               // offsets of the next tile stay in registers
+  __syncthreads();
+  if (use_smem_idx) issue_spans(tile, 0);
+
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    const int next_tile = tile + gridDim.x;
+    if (it > 0) __syncthreads();                   // everyone is done with buffers [nxt] (tile it-1)
+    if (next_tile < ntiles) {
+      store_offs(nxt, regs);
+      load_offs(next_tile + gridDim.x, regs);
+    }
+    __syncthreads();
+    if (use_smem_idx && next_tile < ntiles) issue_spans(next_tile, nxt);
+    if (use_smem_idx) mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
+
+    const int b0 = tile * p.SB;
+    const int sbe = min(p.SB, p.B - b0);
+    const int32_t* so = soff0 + (size_t)cur * noff;
+    const int32_t* si = sidx0 + (size_t)cur * idx_words;
+    const int nseg = sbe * T;
+    for (int s = group; s < nseg; s += ngroups) {
+      const int t = s / sbe, lb = s - t * sbe;
+      const SlsTableDesc td = tabs[t];
+      const int tile_beg = so[t * SB1], tile_end = so[t * SB1 + sbe];
+      const int beg = so[t * SB1 + lb], end = so[t * SB1 + lb + 1];
+      const int a0 = tile_beg & ~3;
+      const bool in_smem = use_smem_idx && (((tile_end - a0 + 3) & ~3) <= p.idx_cap);
+      const float* rows_lane = td.rows + lane * 4;
+      float4 acc;
+      if (in_smem)
+        acc = sls_segment_vec4<true>(rows_lane, (uint32_t)td.n_rows, p.D,
+                                     si + (size_t)t * p.idx_cap - a0, beg, end, p.err_flag);
+      else
+        acc = sls_segment_vec4<false>(rows_lane, (uint32_t)td.n_rows, p.D, td.idx, beg, end,
+                                      p.err_flag);
+      const int64_t b = b0 + lb;
+      float* o = (p.shard_S > 0 ? p.peer_out[b / p.shard_S] + (b % p.shard_S) * p.ld_out
+                                : p.out + b * p.ld_out) + td.dst_col + lane * 4;
+      if (p.vec_store) {
+        *reinterpret_cast<float4*>(o) = acc;
+      } else {
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+      }
     }
   }
 }

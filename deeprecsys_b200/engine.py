@@ -221,6 +221,9 @@ class AccelEngine(object):
             return view.view(np.int32).copy()
         return view.copy()
 
+    def set_option(self, key, value):
+        _lib.check(self.lib.drs_set_option(self._handle, key.encode(), int(value)))
+
     def profile_begin(self, max_steps):
         _lib.check(self.lib.drs_profile_begin(self._handle, int(max_steps)))
 

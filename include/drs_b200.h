@@ -157,6 +157,12 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
 int drs_launch_count(const drs_engine* e, int64_t* n_kernel_launches);
 int drs_hbm_bytes(const drs_engine* e, int64_t* bytes_allocated);
 
+/* Runtime options.  "mlp_chain" (default 1): fuse whole FC stacks into one tcgen05 kernel when
+ * the shapes allow (tensor-core precisions only).  "tap_hidden" (default 0): in chain mode also
+ * store the hidden activations so that drs_fetch_stage can return them.  "gather_ctas_per_sm"
+ * (default 4): K1 runs as a persistent kernel with that many CTAs per SM (0 = one CTA per tile). */
+int drs_set_option(drs_engine* e, const char* key, int64_t value);
+
 /* Per-segment CUDA-event profiling of the served graph, on the engine stream:
  * between begin and end every query records 4 events (start | before K1 |
  * after K1 | end); end returns the summed times of the pre-gather kernels

@@ -17,8 +17,10 @@ from tests.helpers import SMALL, make_case, request
 pytestmark = pytest.mark.gpu
 
 
-def _engine(c, precision="fp32"):
+def _engine(c, precision="fp32", chain=True):
     eng = AccelEngine(args=c.args, max_batch=c.args.max_mini_batch_size, precision=precision)
+    eng.set_option("mlp_chain", int(chain))
+    eng.set_option("tap_hidden", 1)          # stage-level parity needs the hidden activations
     eng.load_parameters(c.tables, c.fcs)
     return eng
 
@@ -163,9 +165,10 @@ def test_offsets_bitexact_variable_lengths():
 
 
 # ---------------------------------------------------------------- tensor-core MLP path
+@pytest.mark.parametrize("chain", [True, False], ids=["chain", "per_layer"])
 @pytest.mark.parametrize("name", ["dlrm_cat", "dlrm_dot", "dlrm_rm2_like", "dlrm_rm3_like", "wnd",
                                   "ncf", "din", "din_many", "dlrm_odd"])
-def test_tf32x3_tensor_core_path_fp32_class_accuracy(name):
+def test_tf32x3_tensor_core_path_fp32_class_accuracy(name, chain):
     """tcgen05 kind::tf32 with hi/lo split operands (3 MMAs per product).  Final
     outputs: same tolerance as the fp32 FFMA path (atol 1e-5).  Hidden layers:
     atol 5e-5 / rtol 2e-4 — the tensor core accumulates in fp32 with
@@ -173,7 +176,7 @@ def test_tf32x3_tensor_core_path_fp32_class_accuracy(name):
     still ~50x tighter than single-pass TF32."""
     mb = 16 if name == "dlrm_rm3_like" else 200
     c = make_case(name, num_batches=1, max_batch=mb)
-    with _engine(c, precision="tf32x3") as eng:
+    with _engine(c, precision="tf32x3", chain=chain) as eng:
         for B in (mb, 3):
             dense, ids, lengths = request(c, 0, B)
             st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)

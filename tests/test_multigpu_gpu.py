@@ -1,0 +1,32 @@
+"""Table-sharded serving across GPUs of one box (needs >= 2 GPUs): K1 stores
+pooled vectors straight into the owner rank's buffer over NVLink; every rank's
+output slice must match the CPU oracle and pooled slices must stay bit-exact."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_table_sharded_two_gpus_matches_oracle(precision):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (have %d)" % n)
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29631",
+           os.path.join(ROOT, "tests", "_shard_worker.py"), precision]
+    proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-4000:]
+    assert proc.stdout.count("DONE") == world, proc.stdout[-4000:]
