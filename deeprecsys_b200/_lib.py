@@ -67,6 +67,12 @@ _SIGNATURES = {
     "drs_enqueue_host": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int,
                                    C.c_void_p]),
     "drs_sync": (C.c_int, [C.c_void_p]),
+    "drs_submit_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                    C.POINTER(C.c_int64)]),
+    "drs_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int, C.c_void_p,
+                                  C.POINTER(C.c_int64)]),
+    "drs_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "drs_lane_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "drs_timer_start": (C.c_int, [C.c_void_p]),
     "drs_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "drs_sparse_lengths_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64,

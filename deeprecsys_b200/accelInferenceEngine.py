@@ -88,6 +88,34 @@ class AccelBackend(object):
             out, _ = self.engine.infer_staged(batch_id, B)
         return out
 
+    # pipelined serving: up to ``depth`` packets in flight (engine lanes overlap the MLP kernels
+    # of one packet with the gather of the next)
+    @property
+    def depth(self):
+        return 1 if self.upload else self.engine.lane_count()
+
+    def submit(self, batch_id, batch_size):
+        if self.upload:
+            return ("done", self.serve(batch_id, batch_size))
+        if not hasattr(self, "_out_pool"):
+            from deeprecsys_b200.engine import pinned_empty
+            self._out_pool = [pinned_empty((int(self.args.max_mini_batch_size), self.spec.out_dim),
+                                           np.float32) for _ in range(self.depth)]
+            self._out_next = 0
+        buf, _owner = self._out_pool[self._out_next]
+        self._out_next = (self._out_next + 1) % len(self._out_pool)
+        import ctypes
+        ticket = self.engine.submit_staged(batch_id, int(batch_size),
+                                           ctypes.c_void_p(buf.ctypes.data))
+        return ("ticket", ticket, buf, int(batch_size))
+
+    def complete(self, handle):
+        if handle[0] == "done":
+            return handle[1]
+        _, ticket, buf, B = handle
+        self.engine.wait(ticket)
+        return buf[:B]
+
     def close(self):
         self.engine.close()
 
@@ -125,32 +153,29 @@ def accelInferenceEngine(args,
 
     inferenceEngineReadyQueue.put(True)
 
-    while True:
-        debugPrint(args, "Accel", "Trying to pull request")
-        request = requestQueue.get()
-        debugPrint(args, "Accel", "Pulled request")
+    # Packets are served in arrival order with up to ``depth`` of them in flight on the GPU;
+    # a response is stamped when its own result has landed in host memory.
+    import collections
+    inflight = collections.deque()
+    pipelined = backend is not None and hasattr(backend, "submit") and backend.depth > 1
+    depth = backend.depth if pipelined else 1
 
-        if request is None:
-            debugPrint(args, "Accel", "Sending final done signal")
-            responseQueue.put(None)
-            if backend is not None:
-                backend.close()
-            return
-
-        start_time = time.time()
+    def finish_oldest():
+        request, start_time, handle = inflight.popleft()
         out_batch_size = 0
-        if backend is not None:
-            try:
-                out = backend.serve(request.batch_id, request.batch_size)
-                out_batch_size = int(out.shape[0])
-                if backend.dump_dir:
-                    np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (
-                        request.epoch, request.batch_id, request.batch_size)), out)
-            except Exception as exc:       # keep serving: the parent counts responses
-                print("[Accel] request failed: %r" % (exc,))
-                sys.stdout.flush()
-        end_time = time.time()
+        try:
+            out = backend.complete(handle)
+            out_batch_size = int(out.shape[0])
+            if backend.dump_dir:
+                np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (
+                    request.epoch, request.batch_id, request.batch_size)), np.array(out))
+        except Exception as exc:           # keep serving: the parent counts responses
+            print("[Accel] request failed: %r" % (exc,))
+            sys.stdout.flush()
+        respond(request, start_time, out_batch_size)
 
+    def respond(request, start_time, out_batch_size):
+        end_time = time.time()
         response = ServiceResponse(consumer_id=engine_id,
                                    epoch=request.epoch,
                                    batch_id=request.batch_id,
@@ -165,3 +190,40 @@ def accelInferenceEngine(args,
                                    sub_id=request.sub_id)
         debugPrint(args, "Accel", "Sending response back")
         responseQueue.put(response)
+
+    while True:
+        if inflight and (len(inflight) >= depth or requestQueue.empty()):
+            finish_oldest()
+            continue
+        debugPrint(args, "Accel", "Trying to pull request")
+        request = requestQueue.get()
+        debugPrint(args, "Accel", "Pulled request")
+
+        if request is None:
+            while inflight:
+                finish_oldest()
+            debugPrint(args, "Accel", "Sending final done signal")
+            responseQueue.put(None)
+            if backend is not None:
+                backend.close()
+            return
+
+        start_time = time.time()
+        if backend is None:
+            respond(request, start_time, 0)
+            continue
+        try:
+            if pipelined:
+                inflight.append((request, start_time,
+                                 backend.submit(request.batch_id, request.batch_size)))
+                continue
+            out = backend.serve(request.batch_id, request.batch_size)
+            out_batch_size = int(out.shape[0])
+            if backend.dump_dir:
+                np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (
+                    request.epoch, request.batch_id, request.batch_size)), out)
+        except Exception as exc:           # keep serving: the parent counts responses
+            print("[Accel] request failed: %r" % (exc,))
+            sys.stdout.flush()
+            out_batch_size = 0
+        respond(request, start_time, out_batch_size)

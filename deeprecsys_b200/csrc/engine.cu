@@ -157,6 +157,7 @@ struct drs_engine {
 
   int64_t launches = 0;
   int64_t hbm_bytes = 0;
+  int64_t submit_seq = 0;
 
   // options (drs_set_option)
   int gather_ctas_per_sm = 4; // > 0: persistent gather with that many CTAs per SM; 0: one CTA per tile
@@ -1240,6 +1241,46 @@ int drs_infer(drs_engine* e, const float* dense, const void* const* idx, int idx
     tm->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0)
                        .count();
   }
+  return DRS_OK;
+}
+
+// Asynchronous submit / wait pair (one submitting thread).  ticket = (sequence << 8) | lane.
+static int64_t make_ticket(drs_engine* e) { return ((++e->submit_seq) << 8) | (int64_t)e->last_lane; }
+
+int drs_submit_staged(drs_engine* e, int batch_id, int batch_size, float* out_pinned,
+                      int64_t* ticket) {
+  CHECK_ARG(e && ticket, "NULL argument");
+  Lane& ln = pick_lane(e);
+  TRY(enqueue_staged_on(e, ln, batch_id, batch_size));
+  if (out_pinned && ln.last_rows > 0)
+    CU(cudaMemcpyAsync(out_pinned, ln.out, (size_t)ln.last_rows * e->out_dim * sizeof(float),
+                       cudaMemcpyDeviceToHost, ln.stream));
+  *ticket = make_ticket(e);
+  return DRS_OK;
+}
+
+int drs_submit_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
+                    const int32_t* const* lengths, int batch_size, float* out_pinned,
+                    int64_t* ticket) {
+  CHECK_ARG(e && ticket, "NULL argument");
+  Lane& ln = pick_lane(e);
+  CU(cudaStreamSynchronize(ln.stream));      // the lane's input slot is reused
+  TRY(enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out_pinned));
+  *ticket = make_ticket(e);
+  return DRS_OK;
+}
+
+int drs_wait(drs_engine* e, int64_t ticket) {
+  CHECK_ARG(e, "engine is NULL");
+  const int lane = (int)(ticket & 0xff);
+  CHECK_ARG(lane >= 0 && lane < e->n_lanes, "bad ticket");
+  CU(cudaSetDevice(e->device));
+  return finish_lane(e, e->lanes[lane]);
+}
+
+int drs_lane_count(const drs_engine* e, int* n_lanes) {
+  CHECK_ARG(e && n_lanes, "NULL argument");
+  *n_lanes = e->n_lanes;
   return DRS_OK;
 }
 

@@ -184,6 +184,21 @@ class AccelEngine(object):
         _lib.check(self.lib.drs_enqueue_host(self._handle, dense_ptr, ids_ptrs, is64, len_ptrs,
                                              int(batch_size), out_ptr))
 
+    def submit_staged(self, batch_id, batch_size, out_ptr=None):
+        """Asynchronous serve of a staged batch; returns a ticket for ``wait``."""
+        t = C.c_int64()
+        _lib.check(self.lib.drs_submit_staged(self._handle, int(batch_id), int(batch_size),
+                                              out_ptr, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        _lib.check(self.lib.drs_wait(self._handle, int(ticket)))
+
+    def lane_count(self):
+        n = C.c_int()
+        _lib.check(self.lib.drs_lane_count(self._handle, C.byref(n)))
+        return n.value
+
     def sync(self):
         _lib.check(self.lib.drs_sync(self._handle))
 

@@ -1,0 +1,146 @@
+"""System-level serving harness for the accel engine (the "inferences/sec at p99"
+half of the metric) for boxes where the reference checkout is not available.
+
+It drives ``accelInferenceEngine`` through the SAME process/Queue protocol as
+the reference orchestrator (/root/reference/DeepRecSys.py:44-138): a bounded
+``accelRequestQueue`` (maxsize 32, DeepRecSys.py:45), one response Queue, one
+ready Queue, ``ServiceRequest`` in, ``ServiceResponse`` out, ``None`` sentinel.
+The load generator follows loadGenerator.py: query sizes from
+``model_batch_size_distribution`` (:20-43: normal / lognormal / fixed, clipped
+to [1, max_mini_batch_size]), Poisson arrivals (:198) — except that
+inter-arrival times are continuous exponentials (sub-millisecond resolution)
+instead of integer milliseconds, because a B200 serves a 1024-item RMC1 query
+in ~0.2 ms.  Latency = inference_end_time - arrival_time, as
+DeepRecSys.py:122-123 computes it.
+
+    python -m deeprecsys_b200.serve --config_file deeprecsys_b200/models/configs/dlrm_rm1.json \
+        --num_batches 32 --max_mini_batch_size 1024 --batch_size_distribution normal \
+        --avg_mini_batch_size 256 --var_mini_batch_size 32 --avg_arrival_rate 0.25 --nepochs 40
+"""
+from __future__ import absolute_import, division, print_function
+
+import json
+import multiprocessing as mp
+import sys
+import time
+
+import numpy as np
+
+from deeprecsys_b200.accelInferenceEngine import accelInferenceEngine
+from deeprecsys_b200.utils.packets import ServiceRequest
+from deeprecsys_b200.utils.utils import cli
+
+
+def query_sizes(args, n, rng):
+    """loadGenerator.py:20-43 (file-based distribution omitted)."""
+    dist = args.batch_size_distribution
+    if dist == "normal":
+        s = rng.normal(args.avg_mini_batch_size, args.var_mini_batch_size, n)
+    elif dist == "lognormal":
+        s = rng.lognormal(args.avg_mini_batch_size, args.var_mini_batch_size, n)
+    elif dist == "fixed":
+        s = np.full(n, args.avg_mini_batch_size, dtype=np.float64)
+    else:
+        raise ValueError("batch_size_distribution %r not supported by this harness" % dist)
+    return np.clip(s, 1, args.max_mini_batch_size).astype(np.int64)
+
+
+def _sleep_until(t):
+    while True:
+        dt = t - time.time()
+        if dt <= 0:
+            return
+        if dt > 0.002:
+            time.sleep(dt - 0.001)      # coarse sleep, then spin (loadGenerator.py:57-64 does the same)
+
+
+def run_system(args, n_queries, arrival_ms, seed=0, warmup_queries=20):
+    """One experiment at a fixed mean inter-arrival time.  Returns a dict of stats."""
+    ctx = mp.get_context("fork")        # DeepRecSys.py uses the default (fork) start method
+    accel_q = ctx.Queue(maxsize=32)     # DeepRecSys.py:45
+    resp_q, ready_q = ctx.Queue(), ctx.Queue()
+    proc = ctx.Process(target=accelInferenceEngine, args=(args, accel_q, 0, resp_q, ready_q))
+    proc.daemon = True
+    proc.start()
+    ready_q.get()                       # loadGenerator.py:76-78
+
+    rng = np.random.RandomState(seed)
+    n_total = n_queries + warmup_queries
+    sizes = query_sizes(args, n_total, rng)
+    gaps = rng.exponential(arrival_ms / 1000.0, n_total)
+    responses = []
+
+    import threading
+
+    def collect():
+        while True:
+            r = resp_q.get()
+            if r is None:
+                return
+            responses.append(r)
+
+    th = threading.Thread(target=collect, daemon=True)
+    th.start()
+    t_next = time.time()
+    t_first = None
+    for i in range(n_total):
+        t_next += gaps[i]
+        _sleep_until(t_next)
+        req = ServiceRequest(batch_id=i % max(1, args.num_batches), epoch=i // max(1, args.num_batches),
+                             batch_size=int(sizes[i]), sub_id=0, total_sub_batches=1,
+                             exp_packet=(i < warmup_queries))
+        req.arrival_time = time.time()
+        if i == warmup_queries:
+            t_first = req.arrival_time
+        accel_q.put(req)                # blocks when the engine falls behind (bounded queue)
+    accel_q.put(None)
+    th.join(timeout=120)
+    proc.join(timeout=60)
+
+    meas = [r for r in responses if not r.exp_packet]
+    lat = np.array([r.inference_end_time - r.arrival_time for r in meas]) * 1e3
+    items = int(sum(r.batch_size for r in meas))
+    failed = sum(1 for r in meas if r.out_batch_size != r.batch_size)
+    span = max(r.inference_end_time for r in meas) - t_first
+    return {
+        "arrival_ms": arrival_ms, "queries": len(meas), "failed": failed, "items": items,
+        "offered_qps": 1000.0 / arrival_ms, "qps": len(meas) / span,
+        "inferences_per_s": items / span,
+        "p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)),
+        "p99_ms": float(np.percentile(lat, 99)), "max_ms": float(lat.max()),
+        "mean_query_size": float(np.mean([r.batch_size for r in meas])),
+    }
+
+
+def sweep(args, rates_ms, n_queries, target_p99_ms=None):
+    """Run the experiment at each mean inter-arrival time; report the best
+    throughput whose p99 meets ``target_p99_ms`` (args.target_latency by default)."""
+    target = float(target_p99_ms if target_p99_ms is not None else args.target_latency)
+    rows = [run_system(args, n_queries, r, seed=17 + i) for i, r in enumerate(rates_ms)]
+    ok = [r for r in rows if r["p99_ms"] <= target and r["failed"] == 0]
+    best = max(ok, key=lambda r: r["inferences_per_s"]) if ok else None
+    return {"target_p99_ms": target, "runs": rows, "best": best}
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    rates, n_queries = None, 2000
+    if "--serve_rates_ms" in argv:
+        i = argv.index("--serve_rates_ms")
+        rates = [float(x) for x in argv[i + 1].split(",")]
+        del argv[i:i + 2]
+    if "--serve_queries" in argv:
+        i = argv.index("--serve_queries")
+        n_queries = int(argv[i + 1])
+        del argv[i:i + 2]
+    args = cli(argv)
+    if not args.model_name:
+        args.model_name = {"dlrm": "rm1"}.get(args.model_type, args.model_type)
+    rates = rates or [args.avg_arrival_rate]
+    out = sweep(args, rates, n_queries)
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -139,6 +139,18 @@ int drs_enqueue_host(drs_engine* e, const float* dense, const void* const* idx, 
                      const int32_t* const* lengths, int batch_size, float* out_pinned);
 int drs_sync(drs_engine* e);
 
+/* Submit / wait pair for pipelined serving: up to drs_lane_count() queries may be in flight
+ * (the copy and MLP kernels of one overlap the gather of the next).  out_pinned (nullable) must
+ * be pinned host memory and stay valid until drs_wait(ticket) returns; drs_wait reports the
+ * SparseLengthsSum enforce flag of that query's lane. */
+int drs_submit_staged(drs_engine* e, int batch_id, int batch_size, float* out_pinned,
+                      int64_t* ticket);
+int drs_submit_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
+                    const int32_t* const* lengths, int batch_size, float* out_pinned,
+                    int64_t* ticket);
+int drs_wait(drs_engine* e, int64_t ticket);
+int drs_lane_count(const drs_engine* e, int* n_lanes);
+
 /* CUDA-event stopwatch on the engine's stream (the stream the kernels run on). */
 int drs_timer_start(drs_engine* e);
 int drs_timer_stop(drs_engine* e, float* elapsed_ms);
