@@ -79,3 +79,55 @@ def request(c, batch_id, batch_size):
     d, l, i = slice_request(c.lX, c.lS_l, c.lS_i, batch_id, batch_size, c.spec.L)
     dense = d if c.spec.m_den > 0 else None
     return dense, [np.ascontiguousarray(x) for x in i], [np.ascontiguousarray(x) for x in l]
+
+
+# ---------------------------------------------------------------------------------------------
+# Golden vectors recorded from the REFERENCE's own model code (tests/golden/make_ref_models.py:
+# the unmodified /root/reference/models/*.py builders driven like inferenceEngine.py drives
+# them, over oracle/caffe2_shim).  Blob names are the reference's tags.
+GOLDEN_MAX_BATCH = 12
+GOLDEN_REQUESTS = [(1, 7), (0, 12), (1, 1)]
+
+
+def load_ref_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_models.npz"))
+
+
+def golden_stages(z, name, batch_id, B, spec):
+    """Map the reference's blob names to the stage dict of oracle.numpy_oracle.forward."""
+    pre = "%s/req_%d_%d/" % (name, batch_id, B)
+
+    def g(tag):
+        return z[pre + tag]
+
+    def mlp_tags(layer_tag, n, out_tag):
+        return [g("%s:::fc%d_z" % (layer_tag, i)) if i < n else g(out_tag) for i in range(1, n + 1)]
+
+    T = spec.T
+    if spec.model_type == "ncf":                       # ncf.py:208-297 table tags
+        pooled = [g("emb:::mf_sls0_z"), g("emb:::mf_sls1_z"), g("emb:::mlp_sls0_z"),
+                  g("emb:::mlp_sls1_z")]
+    else:
+        pooled = [g("emb:::sls%d_z" % t) for t in range(T)]
+    st = {"pooled": np.concatenate(pooled, axis=1), "bot": [], "top": []}
+    mlps = dict(spec.mlps)
+    if spec.model_type == "dlrm":
+        st["bot"] = mlp_tags("bot", len(mlps[0]) - 1, "dense_out")
+        st["interact"] = g("interaction")
+        st["top"] = mlp_tags("top", len(mlps[1]) - 1, "prob_click")
+    elif spec.model_type == "wnd":
+        st["interact"] = g("interaction")
+        st["top"] = mlp_tags("top", len(mlps[1]) - 1, "prob_click")
+    elif spec.model_type == "ncf":
+        st["top"] = mlp_tags("mlpfc", len(mlps[1]) - 1, "mlpfc_out")
+        st["interact"] = g("feat_int")
+        st["out"] = g("prob_click")
+        return st
+    elif spec.model_type == "din":
+        st["bot"] = [g("atten_out")]
+        st["interact"] = g("top_fc_in")
+        st["top"] = mlp_tags("top", len(mlps[1]) - 1, "prob_click")
+    else:
+        raise ValueError(spec.model_type)
+    st["out"] = g("prob_click")
+    return st

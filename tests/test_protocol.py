@@ -146,16 +146,28 @@ SHIM_CPU = "from oracle.cpu_inference_engine import inferenceEngine\n"
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
-def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_path):
+@pytest.mark.parametrize("cpu_engine", ["torch_port", "reference_over_caffe2_shim"])
+def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_path, cpu_engine):
+    """cpu_engine = reference_over_caffe2_shim: every file of the system except
+    accelInferenceEngine.py is the reference's own (DeepRecSys.py, loadGenerator.py,
+    scheduler.py, inferenceEngine.py, models/, data_generator/, utils/), with the Caffe2
+    operator runtime supplied by oracle/caffe2_shim."""
     stage = tmp_path / "drs"
     stage.mkdir()
-    for name in ("DeepRecSys.py", "loadGenerator.py", "scheduler.py", "utils"):
+    names = ["DeepRecSys.py", "loadGenerator.py", "scheduler.py", "utils"]
+    pypath = ROOT
+    if cpu_engine == "reference_over_caffe2_shim":
+        names += ["inferenceEngine.py", "models", "data_generator"]
+        pypath = os.path.join(ROOT, "oracle", "caffe2_shim") + os.pathsep + ROOT
+    else:
+        (stage / "inferenceEngine.py").write_text(SHIM_CPU)
+    for name in names:
         os.symlink(os.path.join(REF, name), stage / name)
     (stage / "accelInferenceEngine.py").write_text(textwrap.dedent(SHIM_ACCEL))
-    (stage / "inferenceEngine.py").write_text(SHIM_CPU)
     dump = tmp_path / "dump"
     dump.mkdir()
-    env = dict(os.environ, PYTHONPATH=ROOT, DRS_ACCEL_DUMP_DIR=str(dump), PYTHONWARNINGS="ignore")
+    env = dict(os.environ, PYTHONPATH=pypath, DRS_ACCEL_DUMP_DIR=str(dump),
+               PYTHONWARNINGS="ignore")
     argv = SMALL_SYSTEM + ["--queue", "--model_accel", "--inference_engines", "1",
                            "--nepochs", "2", "--batch_size_distribution", "normal",
                            "--avg_mini_batch_size", "32", "--var_mini_batch_size", "16",
