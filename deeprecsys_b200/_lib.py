@@ -13,15 +13,17 @@ from . import build as _build
 
 # enums of drs_b200.h
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_COMM = range(6)
-MODEL_DLRM, MODEL_WND, MODEL_NCF, MODEL_DIN = range(4)
+MODEL_DLRM, MODEL_WND, MODEL_NCF, MODEL_DIN, MODEL_MTWND = range(5)
 INTERACT_CAT, INTERACT_DOT = 0, 1
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
-MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE = 0, 1, 2, 16
-STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS = range(6)
+MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE = 0, 1, 2, 16, 4096
+STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS, STAGE_TASK = range(7)
+ABI_VERSION = 2
 SHARD_BLOB_BYTES = 192
 
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
-MODEL_TYPES = {"dlrm": MODEL_DLRM, "wnd": MODEL_WND, "ncf": MODEL_NCF, "din": MODEL_DIN}
+MODEL_TYPES = {"dlrm": MODEL_DLRM, "wnd": MODEL_WND, "ncf": MODEL_NCF, "din": MODEL_DIN,
+               "mtwnd": MODEL_MTWND}
 
 
 class DrsError(RuntimeError):
@@ -39,6 +41,8 @@ class Spec(C.Structure):
         ("interaction_op", C.c_int32), ("interaction_itself", C.c_int32),
         ("max_batch", C.c_int32), ("max_lookups_per_table", C.c_int32),
         ("precision", C.c_int32), ("n_lanes", C.c_int32),
+        ("n_tasks", C.c_int32), ("n_task", C.c_int32), ("ln_task", C.POINTER(C.c_int32)),
+        ("task_sigmoid_layer", C.c_int32),
     ]
 
 
@@ -112,6 +116,10 @@ def load():
         for name, (restype, argtypes) in _SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if a symbol is missing
             fn.restype, fn.argtypes = restype, argtypes
+        if lib.drs_abi_version() != ABI_VERSION:
+            raise ImportError("libdrs_b200.so has ABI version %d, this binding needs %d: rebuild "
+                              "with `python -m deeprecsys_b200.build`"
+                              % (lib.drs_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

@@ -126,6 +126,7 @@ struct Lane {
   float* F = nullptr;             // NCF: [cap_rows, D + tower_out]
   float* C = nullptr;             // DIN: [n_units, cap_rows, 3D]
   std::vector<float*> ybot, ytop, yfin;   // per-layer outputs
+  std::vector<float*> ytask;              // MT-WnD: per-layer outputs [n_tasks, cap, width]
   float* out = nullptr;
   int* d_err = nullptr;
   int* h_err = nullptr;           // pinned
@@ -147,6 +148,8 @@ struct drs_engine {
   std::vector<float*> tables;
   std::vector<char> table_loaded;
   Mlp bot, top, fin;          // DIN: bot = attention MLP batched over n_units
+  Mlp task;                   // MT-WnD: task heads batched over n_tasks (own weights each)
+  std::vector<int32_t> ln_task;
 
   int n_lanes = 2;
   Lane lanes[kMaxLanes];
@@ -467,6 +470,9 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
   *smem_out = sls_smem_bytes(T, SB, idx_cap, D, dot);
 }
 
+// Note: making the gather of query i+1 wait for the gather of query i (so that lanes overlap
+// only MLP/copy work with the HBM-bound gather) was measured slower on B200 than letting two
+// gathers share the chip (RMC1 16384 samples, 3 lanes: 60.5 vs 65.6 M inf/s).
 int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
   SlsLaunch p{};
   p.tables = s.descs; p.T = (int)e->owned.size(); p.B = B; p.D = e->D;
@@ -560,6 +566,7 @@ int check_ready(drs_engine* e) {
   if (!e->bot.all_loaded()) return fail(DRS_ERR_STATE, "bottom/attention MLP weights not loaded");
   if (!e->top.all_loaded()) return fail(DRS_ERR_STATE, "top MLP weights not loaded");
   if (!e->fin.all_loaded()) return fail(DRS_ERR_STATE, "final FC weights not loaded");
+  if (!e->task.all_loaded()) return fail(DRS_ERR_STATE, "task-head MLP weights not loaded");
   return DRS_OK;
 }
 
@@ -618,6 +625,39 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
         TRY(shard_wait(e, ln, 0, ln.epoch));
       }
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
+      break;
+    }
+    case DRS_MODEL_MTWND: {
+      // multi_task_wnd.py:285-316: Concat(dense_in, e_0..e_{T-1}) -> shared top MLP (all ReLU)
+      // -> n_tasks heads, each its own weights, all reading the shared top output
+      if (rows > 0) {
+        k_copy_cols<<<ew_grid((int64_t)rows * e->m_den), 256, 0, ln.stream>>>(
+            dense, e->m_den, ln.R, e->ld_R, rows, e->m_den);
+        CU(cudaGetLastError());
+        e->launches += 1;
+      }
+      PROF_MARK(1);
+      TRY(launch_gather(e, ln, s, B, false));
+      PROF_MARK(2);
+      if (e->world > 1) {
+        TRY(shard_signal(e, ln, 0, ln.epoch));
+        TRY(shard_wait(e, ln, 0, ln.epoch));
+      }
+      TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
+      if (rows > 0) {
+        const int nl = (int)e->task.layers.size();
+        const int nt = e->spec.n_tasks;
+        const float* in = ln.ytop.back();
+        int64_t ld_in = e->top.layers.back().out, bs_in = 0, rows_in = cap;
+        for (int i = 0; i < nl; ++i) {
+          Layer& l = e->task.layers[i];
+          float* y = ln.ytask[i];
+          int64_t ldy = l.out, bsy = cap * l.out;
+          if (i == nl - 1) { y = ln.out; ldy = (int64_t)nt * l.out; bsy = l.out; }  // heads side by side
+          TRY(launch_fc(e, ln, l, in, ld_in, bs_in, rows_in, y, ldy, bsy, rows));
+          in = y; ld_in = ldy; bs_in = bsy; rows_in = (int64_t)nt * cap;
+        }
+      }
       break;
     }
     case DRS_MODEL_NCF: {
@@ -864,6 +904,9 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   e->T = spec->n_tables;
   e->D = spec->emb_dim;
   e->n_lanes = spec->n_lanes > 0 ? spec->n_lanes : 2;
+  // With >= 3 lanes two gathers are usually in flight at once: 3 persistent CTAs per SM each
+  // measured best on B200 (RMC1, 16384 samples: 65.3 M inf/s vs 63.0 with 4; 2 lanes: 4 is best).
+  if (!getenv("DRS_GATHER_CTAS_PER_SM")) e->gather_ctas_per_sm = e->n_lanes >= 3 ? 3 : 4;
   e->table_rows.assign(spec->table_rows, spec->table_rows + spec->n_tables);
   if (spec->n_bot > 0 && spec->ln_bot) e->ln_bot.assign(spec->ln_bot, spec->ln_bot + spec->n_bot);
   e->ln_top.assign(spec->ln_top, spec->ln_top + spec->n_top);
@@ -921,6 +964,27 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
       e->ld_R = e->ln_top[0];
       e->gather_into_R = true;
       TRYB(alloc_mlp_params(e, e->top, e->ln_top, 1, kActSigmoid));
+      break;
+    }
+    case DRS_MODEL_MTWND: {
+      CHECKB(e->ln_bot.size() == 1, "MT-Wide&Deep has no bottom MLP layers (arch_mlp_bot = m_den)");
+      e->m_den = e->ln_bot[0];
+      CHECKB(e->ln_top[0] == T * D + e->m_den, "top mlp input %d != T*D + m_den = %d",
+             e->ln_top[0], T * D + e->m_den);                    // multi_task_wnd.py:353
+      CHECKB(spec->n_tasks >= 1 && spec->n_task >= 2 && spec->ln_task,
+             "MT-Wide&Deep needs num_multi_tasks >= 1 and a task MLP");
+      e->ln_task.assign(spec->ln_task, spec->ln_task + spec->n_task);
+      e->spec.ln_task = e->ln_task.data();
+      CHECKB(e->ln_top.back() == e->ln_task.front(),
+             "Shared top layer and task MLP layers must have same input/output dimension");  // :362
+      CHECKB(spec->task_sigmoid_layer >= 0 && spec->task_sigmoid_layer <= spec->n_task - 1,
+             "task_sigmoid_layer out of range");
+      e->ld_R = e->ln_top[0];
+      e->gather_into_R = true;
+      TRYB(alloc_mlp_params(e, e->top, e->ln_top, 1, kActRelu));        // create_mlp(ln_top, -1)
+      TRYB(alloc_mlp_params(e, e->task, e->ln_task, spec->n_tasks, kActRelu));
+      if (spec->task_sigmoid_layer > 0)
+        e->task.layers[spec->task_sigmoid_layer - 1].act = kActSigmoid;
       break;
     }
     case DRS_MODEL_NCF: {
@@ -984,11 +1048,14 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
     TRYB(alloc_mlp_acts(e, e->bot, ln.ybot));
     TRYB(alloc_mlp_acts(e, e->top, ln.ytop));
     TRYB(alloc_mlp_acts(e, e->fin, ln.yfin));
-    ln.out = (spec->model_type == DRS_MODEL_NCF) ? ln.yfin.back() : ln.ytop.back();
+    TRYB(alloc_mlp_acts(e, e->task, ln.ytask));
+    ln.out = (spec->model_type == DRS_MODEL_NCF) ? ln.yfin.back()
+           : (spec->model_type == DRS_MODEL_MTWND) ? ln.ytask.back() : ln.ytop.back();
     TRYB(alloc_input_set(e, ln.slot, maxB, maxB, caps, true, ln.stream));
   }
   Mlp& lastm = (spec->model_type == DRS_MODEL_NCF) ? e->fin : e->top;
   e->out_dim = lastm.layers.back().out;
+  if (spec->model_type == DRS_MODEL_MTWND) e->out_dim = spec->n_tasks * e->task.layers.back().out;
 
   e->tables.assign(T, nullptr);
   e->table_loaded.assign(T, 0);
@@ -1020,7 +1087,7 @@ int drs_destroy(drs_engine* e) {
   for (int q = 0; q < e->world; ++q)
     if (q != e->rank && e->peer_slab[q]) cudaIpcCloseMemHandle(e->peer_slab[q]);
   for (float* t : e->tables) cudaFree(t);
-  for (Mlp* m : {&e->bot, &e->top, &e->fin})
+  for (Mlp* m : {&e->bot, &e->top, &e->fin, &e->task})
     for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wsplit); }
   for (auto& kv : e->staged) free_input_set(kv.second);
   for (int i = 0; i < kMaxLanes; ++i) {
@@ -1028,7 +1095,7 @@ int drs_destroy(drs_engine* e) {
     if (!e->gather_into_R) cudaFree(ln.R);
     if (e->dot) cudaFree(ln.P);
     cudaFree(ln.dense_out); cudaFree(ln.F); cudaFree(ln.C);
-    for (auto* v : {&ln.ybot, &ln.ytop, &ln.yfin}) for (float* p : *v) cudaFree(p);
+    for (auto* v : {&ln.ybot, &ln.ytop, &ln.yfin, &ln.ytask}) for (float* p : *v) cudaFree(p);
     free_input_set(ln.slot);
     cudaFree(ln.d_err);
     if (ln.h_err) cudaFreeHost(ln.h_err);
@@ -1081,6 +1148,11 @@ int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const floa
            mlp_id - DRS_MLP_ATTN_BASE < e->n_units) {
     m = &e->bot;
     unit = mlp_id - DRS_MLP_ATTN_BASE;
+  }
+  else if (mlp_id >= DRS_MLP_TASK_BASE && e->spec.model_type == DRS_MODEL_MTWND &&
+           mlp_id - DRS_MLP_TASK_BASE < e->spec.n_tasks) {
+    m = &e->task;
+    unit = mlp_id - DRS_MLP_TASK_BASE;
   }
   CHECK_ARG(m != nullptr, "mlp_id %d does not exist in this model", mlp_id);
   CHECK_ARG(layer >= 0 && layer < (int)m->layers.size(), "layer %d out of range [0,%d)", layer,
@@ -1431,6 +1503,17 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
                   "mode: drs_set_option(e, \"tap_hidden\", 1) before serving to tap them");
         src = ln.ytop[layer]; ld = l.out;
       }
+      break;
+    }
+    case DRS_STAGE_TASK: {
+      CHECK_ARG(e->spec.model_type == DRS_MODEL_MTWND, "model has no task heads");
+      const int tk = layer / 256, k = layer % 256;
+      CHECK_ARG(tk >= 0 && tk < e->spec.n_tasks && k >= 0 && k < (int)e->task.layers.size(),
+                "task %d / layer %d out of range", tk, k);
+      const Layer& l = e->task.layers[k];
+      c = l.out;
+      if (k == (int)e->task.layers.size() - 1) { src = ln.out + (int64_t)tk * l.out; ld = e->out_dim; }
+      else { src = ln.ytask[k] + (int64_t)tk * e->spec.max_batch * l.out; ld = l.out; }
       break;
     }
     case DRS_STAGE_OUT:

@@ -58,6 +58,10 @@ class AccelEngine(object):
         cs.max_lookups_per_table = int(max_lookups_per_table or self.max_batch * max(1, s.L))
         cs.precision = _lib.PRECISIONS[precision]
         cs.n_lanes = int(lanes)
+        if s.model_type == "mtwnd":
+            self._task = (C.c_int32 * len(s.ln_task))(*s.ln_task)
+            cs.n_tasks, cs.n_task, cs.ln_task = s.n_tasks, len(s.ln_task), self._task
+            cs.task_sigmoid_layer = s.task_sigmoid_layer
         self._handle = C.c_void_p()
         _lib.check(self.lib.drs_create(C.byref(cs), int(device), C.byref(self._handle)))
         self.out_dim = s.out_dim

@@ -10,6 +10,10 @@ Dimension rules per model (reference file:line):
         final FC = [D + top[-2], top[-1]].
   din   models/din.py:246-258,346-359    attention MLP = [3D] + arch_mlp_bot + [D]
         per behaviour table (tables 1..T-3); top input = 4D.
+  mtwnd models/multi_task_wnd.py:304-316,340-362  WnD trunk with an all-ReLU shared top MLP,
+        then num_multi_tasks heads of widths arch_mlp_tasks (own weights each); every head is
+        built with sigmoid_layer = len(ln_top) - 1, i.e. the Sigmoid lands on task layer
+        len(arch_mlp_top) whatever the head's depth.  Output = heads side by side.
 
 Parameter draw order (global legacy numpy RNG, after datagen inputs+targets):
 tables in index order (uniform(-sqrt(1/n), sqrt(1/n)), drawn float64 then cast,
@@ -75,6 +79,25 @@ class ModelSpec(object):
             tower = self.ln_top[:-1]
             self.mlps = [(_lib.MLP_TOP, tower), (_lib.MLP_FINAL, [D + tower[-1], self.ln_top[-1]])]
             self.sigmoid_last = False
+        elif self.model_type == "mtwnd":
+            if self.interaction_op != "cat" or len(arch_bot) != 1:
+                raise ValueError("multi-task wide&deep needs cat interaction and a single "
+                                 "arch_mlp_bot width")
+            self.m_den, self.ln_bot = arch_bot[0], [arch_bot[0]]
+            self.ln_top = [T * D + arch_bot[0]] + arch_top
+            self.ln_task = _ints(args.arch_mlp_tasks)
+            self.n_tasks = int(args.num_multi_tasks)
+            if self.ln_top[-1] != self.ln_task[0]:
+                raise ValueError("Shared top layer and task MLP layers must have same "
+                                 "input/output dimension")          # multi_task_wnd.py:362
+            if self.n_tasks < 1:
+                raise ValueError("num_multi_tasks must be >= 1")
+            self.task_sigmoid_layer = len(self.ln_top) - 1         # sigmoid_top, :396
+            if self.task_sigmoid_layer > len(self.ln_task) - 1:
+                self.task_sigmoid_layer = 0                        # never reached: all ReLU
+            self.mlps = [(_lib.MLP_TOP, self.ln_top)]
+            self.mlps += [(_lib.MLP_TASK_BASE + i, self.ln_task) for i in range(self.n_tasks)]
+            self.sigmoid_last = False
         else:  # din
             if T < 4:
                 raise ValueError("DIN needs at least 4 embedding tables")
@@ -86,6 +109,8 @@ class ModelSpec(object):
             self.mlps.append((_lib.MLP_TOP, self.ln_top))
             self.sigmoid_last = False
         self.out_dim = self.mlps[-1][1][-1]
+        if self.model_type == "mtwnd":
+            self.out_dim = self.n_tasks * self.ln_task[-1]
 
     # ---- algorithmic work per sample (DESIGN.md / SURVEY 8d)
     def gather_bytes_per_sample(self, fused=True):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRS_ABI_VERSION 1
+#define DRS_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -40,8 +40,10 @@ enum {
   DRS_ERR_COMM = 5         /* peer-memory / multi-GPU exchange setup failure */
 };
 
-/* model graphs (reference: models/dlrm_s_caffe2.py, wide_and_deep.py, ncf.py, din.py) */
-enum { DRS_MODEL_DLRM = 0, DRS_MODEL_WND = 1, DRS_MODEL_NCF = 2, DRS_MODEL_DIN = 3 };
+/* model graphs (reference: models/dlrm_s_caffe2.py, wide_and_deep.py, ncf.py, din.py,
+ * multi_task_wnd.py) */
+enum { DRS_MODEL_DLRM = 0, DRS_MODEL_WND = 1, DRS_MODEL_NCF = 2, DRS_MODEL_DIN = 3,
+       DRS_MODEL_MTWND = 4 };
 
 /* arch_interaction_op (dlrm_s_caffe2.py:334-365) */
 enum { DRS_INTERACT_CAT = 0, DRS_INTERACT_DOT = 1 };
@@ -55,7 +57,8 @@ enum {
   DRS_MLP_BOT = 0,         /* DLRM bottom MLP (dlrm_s_caffe2.py:376)                        */
   DRS_MLP_TOP = 1,         /* DLRM/WnD/DIN top MLP; NCF: the MLP tower ln_top[:-1] (ncf.py:332) */
   DRS_MLP_FINAL = 2,       /* NCF final FC over [Zmf, tower] (ncf.py:339-343)               */
-  DRS_MLP_ATTN_BASE = 16   /* DIN attention unit i -> DRS_MLP_ATTN_BASE + i (din.py:260-278) */
+  DRS_MLP_ATTN_BASE = 16,  /* DIN attention unit i -> DRS_MLP_ATTN_BASE + i (din.py:260-278) */
+  DRS_MLP_TASK_BASE = 4096 /* MT-WnD task head i -> DRS_MLP_TASK_BASE + i (multi_task_wnd.py:304-316) */
 };
 
 /* stage taps for drs_fetch_stage (stage-level parity) */
@@ -65,7 +68,8 @@ enum {
   DRS_STAGE_INTERACT = 2,  /* top-MLP input [B, ln_top[0]]                   */
   DRS_STAGE_TOP = 3,       /* layer k output of the top MLP                  */
   DRS_STAGE_OUT = 4,       /* final output [B, out_dim]                      */
-  DRS_STAGE_OFFSETS = 5    /* int32 offsets [T, B+1] reinterpret as float bits (bit-exact bucketing check) */
+  DRS_STAGE_OFFSETS = 5,   /* int32 offsets [T, B+1] reinterpret as float bits (bit-exact bucketing check) */
+  DRS_STAGE_TASK = 6       /* MT-WnD: layer (task * 256 + k) = output of layer k of task head `task` */
 };
 
 typedef struct drs_engine drs_engine;
@@ -88,6 +92,12 @@ typedef struct {
   int32_t max_lookups_per_table; /* largest sum(lengths) of one table in one query           */
   int32_t precision;             /* DRS_PREC_*                                               */
   int32_t n_lanes;               /* concurrent query lanes (stream + activation set); 0 = default 2 */
+  /* MT-WnD only (multi_task_wnd.py:304-316, :358-362); zero for the other graphs */
+  int32_t n_tasks;               /* num_multi_tasks: task heads above the shared top MLP     */
+  int32_t n_task;                /* number of widths in ln_task                              */
+  const int32_t* ln_task;        /* arch_mlp_tasks; ln_task[0] == ln_top[n_top-1]            */
+  int32_t task_sigmoid_layer;    /* 1-based task layer that gets Sigmoid (the reference passes
+                                    sigmoid_top = len(ln_top) - 1 to every head), 0 = none    */
 } drs_spec;
 
 /* per-call timing, milliseconds */

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE = 0, 1, 2, 16
+MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE = 0, 1, 2, 16, 4096
 
 
 class TorchCpuModel(object):
@@ -37,11 +37,12 @@ class TorchCpuModel(object):
         return out
 
     @staticmethod
-    def _mlp(x, layers, sigmoid_last=False):
+    def _mlp(x, layers, sigmoid_last=False, sigmoid_layer=0):
         n = len(layers)
         for i, (W, b) in enumerate(layers):
             x = torch.addmm(b, x, W.t())
-            x = torch.sigmoid(x) if (sigmoid_last and i == n - 1) else torch.relu(x)
+            sig = (sigmoid_last and i == n - 1) or (sigmoid_layer and i == sigmoid_layer - 1)
+            x = torch.sigmoid(x) if sig else torch.relu(x)
         return x
 
     def pool(self, ids, lengths):
@@ -75,6 +76,12 @@ class TorchCpuModel(object):
         if s.model_type == "wnd":
             R = torch.cat([torch.as_tensor(dense)] + pooled, dim=1)
             return self._mlp(R, self._layers(MLP_TOP), sigmoid_last=True)
+        if s.model_type == "mtwnd":
+            R = torch.cat([torch.as_tensor(dense)] + pooled, dim=1)
+            shared = self._mlp(R, self._layers(MLP_TOP))
+            heads = [self._mlp(shared, self._layers(MLP_TASK_BASE + k),
+                               sigmoid_layer=s.task_sigmoid_layer) for k in range(s.n_tasks)]
+            return torch.cat(heads, dim=1)
         if s.model_type == "ncf":
             zmf = pooled[0] + pooled[1]
             tower = self._mlp(torch.cat([pooled[2], pooled[3]], dim=1), self._layers(MLP_TOP))

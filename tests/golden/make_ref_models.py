@@ -51,14 +51,7 @@ WRAPPERS = {
     "mtwnd": (ref_engine.MT_Wide_and_Deep_Wrapper, "mtwnd"),
 }
 
-# extra cases that are not in tests/helpers.SMALL
-EXTRA = {
-    "mtwnd": ["--model_type", "mtwnd", "--arch_embedding_size", "-".join(["300"] * 5),
-              "--arch_sparse_feature_size", "16", "--arch_mlp_bot", "24",
-              "--arch_mlp_top", "64-32", "--arch_mlp_tasks", "32-16-1",
-              "--arch_interaction_op", "cat", "--num_indices_per_lookup", "1",
-              "--num_multi_tasks", "3"],
-}
+EXTRA = {}
 # the reference's MT-WnD queue mode is broken (multi_task_wnd.py:111 calls FeedBlobWrapper
 # with one argument), so it is recorded through the standalone path
 # (inferenceEngine.py:137-173: model.mtwnd.run(lX[j], lS_l[j], lS_i[j]) on whole batches)
@@ -160,6 +153,8 @@ def engine_flow(name, batch_id, B):
 def main():
     arrays = {}
     for name in sorted(SMALL):
+        if name in STANDALONE and name != "dlrm_cat":
+            continue                                   # queue mode broken in the reference
         res, args = direct_flow(name)
         arrays.update(res)
         print("%-16s %-5s blobs/request=%d" % (name, args.model_type,

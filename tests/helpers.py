@@ -49,6 +49,11 @@ SMALL = {
             "--user_behavior_tables", "0", "--arch_sparse_feature_size", "32",
             "--arch_mlp_bot", "1", "--arch_mlp_top", "200-80-2", "--arch_interaction_op", "cat",
             "--num_indices_per_lookup", "3"],
+    "mtwnd": ["--model_type", "mtwnd", "--arch_embedding_size", "-".join(["300"] * 5),
+              "--arch_sparse_feature_size", "16", "--arch_mlp_bot", "24",
+              "--arch_mlp_top", "64-32", "--arch_mlp_tasks", "32-16-1",
+              "--arch_interaction_op", "cat", "--num_indices_per_lookup", "1",
+              "--num_multi_tasks", "3"],
     "din_many": ["--model_type", "din", "--arch_embedding_size", "1000-100-2000-2000",
                  "--user_behavior_tables", "10", "--arch_sparse_feature_size", "32",
                  "--arch_mlp_bot", "8-4", "--arch_mlp_top", "200-80-2",
@@ -93,9 +98,19 @@ def load_ref_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_models.npz"))
 
 
+# cases recorded through the reference's standalone path (whole batches, no queues): the
+# reference's MT-WnD queue mode is broken (multi_task_wnd.py:111)
+GOLDEN_STANDALONE = {"mtwnd": [(0, GOLDEN_MAX_BATCH), (1, GOLDEN_MAX_BATCH)]}
+
+
+def golden_requests(name):
+    return GOLDEN_STANDALONE.get(name, GOLDEN_REQUESTS)
+
+
 def golden_stages(z, name, batch_id, B, spec):
     """Map the reference's blob names to the stage dict of oracle.numpy_oracle.forward."""
-    pre = "%s/req_%d_%d/" % (name, batch_id, B)
+    tag = name + "@standalone" if name in GOLDEN_STANDALONE else name
+    pre = "%s/req_%d_%d/" % (tag, batch_id, B)
 
     def g(tag):
         return z[pre + tag]
@@ -118,6 +133,14 @@ def golden_stages(z, name, batch_id, B, spec):
     elif spec.model_type == "wnd":
         st["interact"] = g("interaction")
         st["top"] = mlp_tags("top", len(mlps[1]) - 1, "prob_click")
+    elif spec.model_type == "mtwnd":                   # multi_task_wnd.py:407-420 tags
+        st["interact"] = g("interaction")
+        st["top"] = mlp_tags("top", len(mlps[1]) - 1, "shared_dense")
+        n_task_layers = len(spec.ln_task) - 1
+        st["tasks"] = [mlp_tags("task_%d" % k, n_task_layers, "task_outs_%d" % k)
+                       for k in range(spec.n_tasks)]
+        st["out"] = np.concatenate([t[-1] for t in st["tasks"]], axis=1)
+        return st
     elif spec.model_type == "ncf":
         st["top"] = mlp_tags("mlpfc", len(mlps[1]) - 1, "mlpfc_out")
         st["interact"] = g("feat_int")

@@ -39,7 +39,7 @@ def _check_stages(c, eng, st, B, fc_atol=1e-5, fc_rtol=1e-4):
         D = spec.D
         assert np.array_equal(inter[:, D:], st["interact"][:, D:])
         np.testing.assert_allclose(inter[:, :D], st["interact"][:, :D], rtol=fc_rtol, atol=fc_atol)
-    elif spec.model_type == "wnd":
+    elif spec.model_type in ("wnd", "mtwnd"):
         assert np.array_equal(inter, st["interact"]), "wnd cat must be exact"
     else:
         np.testing.assert_allclose(inter, st["interact"], rtol=fc_rtol, atol=fc_atol)
@@ -50,6 +50,10 @@ def _check_stages(c, eng, st, B, fc_atol=1e-5, fc_rtol=1e-4):
     for k, ref in enumerate(st["top"]):
         np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_TOP, k), ref, rtol=fc_rtol,
                                    atol=fc_atol)
+    for tk, head in enumerate(st.get("tasks", [])):
+        for k, ref in enumerate(head):
+            np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_TASK, tk * 256 + k), ref,
+                                       rtol=fc_rtol, atol=fc_atol)
     out = eng.fetch_stage(_lib.STAGE_OUT)
     np.testing.assert_allclose(out, st["out"], rtol=fc_rtol, atol=fc_atol)
 

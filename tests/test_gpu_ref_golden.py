@@ -13,7 +13,7 @@ import pytest
 
 from deeprecsys_b200 import _lib
 from deeprecsys_b200.engine import AccelEngine
-from tests.helpers import (GOLDEN_MAX_BATCH, GOLDEN_REQUESTS, SMALL, golden_stages,
+from tests.helpers import (GOLDEN_MAX_BATCH, SMALL, golden_requests, golden_stages,
                            load_ref_golden, make_case, request)
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +28,7 @@ def _check(c, eng, ref, B, atol_out, atol_hidden, rtol):
         "pooled vectors are not bit-identical to the reference's SparseLengthsSum blobs"
     inter = eng.fetch_stage(_lib.STAGE_INTERACT)
     assert inter.shape == ref["interact"].shape
-    if spec.model_type == "wnd":
+    if spec.model_type in ("wnd", "mtwnd"):
         assert np.array_equal(inter, ref["interact"])
     elif spec.model_type == "dlrm" and spec.interaction_op == "cat":
         assert np.array_equal(inter[:, spec.D:], ref["interact"][:, spec.D:])
@@ -36,8 +36,12 @@ def _check(c, eng, ref, B, atol_out, atol_hidden, rtol):
                                    atol=atol_hidden)
     else:
         np.testing.assert_allclose(inter, ref["interact"], rtol=rtol, atol=atol_hidden)
+    for tk, head in enumerate(ref.get("tasks", [])):
+        for k, want in enumerate(head):
+            np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_TASK, tk * 256 + k), want,
+                                       rtol=rtol, atol=atol_hidden)
     for k, want in enumerate(ref["top"]):
-        last = (k == len(ref["top"]) - 1) and spec.model_type != "ncf"
+        last = (k == len(ref["top"]) - 1) and spec.model_type not in ("ncf", "mtwnd")
         np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_TOP, k), want, rtol=rtol,
                                    atol=atol_out if last else atol_hidden)
     np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_OUT), ref["out"], rtol=rtol,
@@ -55,7 +59,7 @@ def test_cuda_path_reproduces_reference_blobs(name, precision, atol_out, atol_hi
         for j in range(2):                                   # staged like the engine process
             dense, ids, lengths = request(c, j, GOLDEN_MAX_BATCH)
             eng.stage_batch(j, dense, [i.astype(np.int64) for i in ids], lengths)
-        for batch_id, B in GOLDEN_REQUESTS:
+        for batch_id, B in golden_requests(name):
             ref = golden_stages(Z, name, batch_id, B, c.spec)
             # host path (run_queues equivalent)
             dense, ids, lengths = request(c, batch_id, B)

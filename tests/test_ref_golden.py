@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from oracle import numpy_oracle as O
-from tests.helpers import (GOLDEN_MAX_BATCH, GOLDEN_REQUESTS, SMALL, golden_stages,
+from tests.helpers import (GOLDEN_MAX_BATCH, SMALL, golden_requests, golden_stages,
                            load_ref_golden, make_case, request)
 
 Z = load_ref_golden()
@@ -27,7 +27,7 @@ def _close(a, b):
 @pytest.mark.parametrize("name", sorted(SMALL))
 def test_oracle_reproduces_reference_blobs(name):
     c = make_case(name, num_batches=2, max_batch=GOLDEN_MAX_BATCH, seed=123)
-    for batch_id, B in GOLDEN_REQUESTS:
+    for batch_id, B in golden_requests(name):
         dense, ids, lengths = request(c, batch_id, B)
         st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
         ref = golden_stages(Z, name, batch_id, B, c.spec)
@@ -42,6 +42,11 @@ def test_oracle_reproduces_reference_blobs(name):
             assert len(st[key]) == len(ref[key]), key
             for a, b in zip(st[key], ref[key]):
                 _close(a, b)
+        for head, ref_head in zip(st.get("tasks", []), ref.get("tasks", [])):
+            assert len(head) == len(ref_head)
+            for a, b in zip(head, ref_head):
+                _close(a, b)
+        assert len(st.get("tasks", [])) == len(ref.get("tasks", []))
         _close(st["out"], ref["out"])
         assert st["out"].shape == (B, c.spec.out_dim)
 
