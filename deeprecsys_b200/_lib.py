@@ -56,6 +56,7 @@ _SIGNATURES = {
     "drs_last_error": (C.c_char_p, []),
     "drs_abi_version": (C.c_int, []),
     "drs_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "drs_device_numa_node": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "drs_create": (C.c_int, [C.POINTER(Spec), C.c_int, _PP]),
     "drs_destroy": (C.c_int, [C.c_void_p]),
     "drs_out_dim": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

@@ -54,9 +54,10 @@ class AccelBackend(object):
 
     def __init__(self, args):
         from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
-        from deeprecsys_b200.engine import AccelEngine
+        from deeprecsys_b200.engine import AccelEngine, bind_to_device_numa_node
 
         self.args = args
+        bind_to_device_numa_node(int(getattr(args, "accel_device", 0)))
         gen = DLRMDataGenerator(args)
         (self.nbatches, self.lX, self.lS_l, self.lS_i) = gen.generate_input_data()
         (_, self.lT) = gen.generate_output_data()          # consumes the RNG like the CPU engine

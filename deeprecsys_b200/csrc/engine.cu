@@ -23,6 +23,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cctype>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -552,7 +553,7 @@ int shard_signal(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
 
 int shard_wait(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
   const int li = (int)(&ln - e->lanes);
-  k_shard_wait<<<1, 32, 0, ln.stream>>>(flag_ptr(e, e->rank, li, which), e->world, epoch);
+  k_shard_wait<<<1, 32, 0, ln.stream>>>(flag_ptr(e, e->rank, li, which), e->world, epoch, ln.d_err);
   CU(cudaGetLastError());
   e->launches += 1;
   return DRS_OK;
@@ -739,9 +740,13 @@ int finish_lane(drs_engine* e, Lane& ln) {
   (void)e;
   CU(cudaStreamSynchronize(ln.stream));
   if (*ln.h_err) {
+    const int what = *ln.h_err;
     *ln.h_err = 0;
     cudaMemsetAsync(ln.d_err, 0, sizeof(int), ln.stream);
     cudaStreamSynchronize(ln.stream);
+    if (what == 2)
+      return fail(DRS_ERR_COMM, "table-sharded exchange timed out waiting for a peer rank's "
+                                "flag (a peer died, or ranks served different queries)");
     return fail(DRS_ERR_INDEX,
                 "SparseLengthsSum enforce failed: index out of range, negative length, or "
                 "sum(lengths) != len(indices)");
@@ -860,6 +865,22 @@ int drs_abi_version(void) { return DRS_ABI_VERSION; }
 int drs_device_count(int* n_out) {
   CHECK_ARG(n_out, "n_out is NULL");
   CU(cudaGetDeviceCount(n_out));
+  return DRS_OK;
+}
+
+int drs_device_numa_node(int device, int* node_out) {
+  CHECK_ARG(node_out, "node_out is NULL");
+  *node_out = -1;
+  char bus[32] = {0};
+  CU(cudaDeviceGetPCIBusId(bus, sizeof(bus), device));
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);      // sysfs uses lower-case hex
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  if (FILE* f = fopen(path, "r")) {
+    int node = -1;
+    if (fscanf(f, "%d", &node) == 1) *node_out = node;
+    fclose(f);
+  }
   return DRS_OK;
 }
 

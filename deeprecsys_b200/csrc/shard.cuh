@@ -28,14 +28,32 @@ __global__ void k_shard_signal(const ShardFlags f, uint32_t epoch) {
   }
 }
 
-// spin until own_flags[q] >= epoch for every q
-__global__ void k_shard_wait(const uint32_t* own_flags, int world, uint32_t epoch) {
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// spin until own_flags[q] >= epoch for every q.  The spin is bounded (kShardWaitTimeoutNs): a
+// peer that died or diverged must not leave this GPU spinning forever — the wait gives up, raises
+// the lane's error flag (reported as DRS_ERR_COMM by the host) and lets the stream drain.
+constexpr uint64_t kShardWaitTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__global__ void k_shard_wait(const uint32_t* own_flags, int world, uint32_t epoch,
+                             int* comm_err_flag) {
   const int q = threadIdx.x;
   if (q < world) {
+    const uint64_t t0 = global_timer_ns();
     uint32_t v;
-    do {
+    for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(own_flags + q) : "memory");
-    } while ((int32_t)(v - epoch) < 0);
+      if ((int32_t)(v - epoch) >= 0) break;
+      if (global_timer_ns() - t0 > kShardWaitTimeoutNs) {
+        if (comm_err_flag) *comm_err_flag = 2;
+        break;
+      }
+      __nanosleep(200);
+    }
   }
   __syncthreads();
   __threadfence_system();

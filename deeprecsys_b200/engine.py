@@ -279,6 +279,37 @@ class AccelEngine(object):
         return n.value
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_device_numa_node(device):
+    """Pin this process to the CPUs of the NUMA node GPU ``device`` is attached to, so that the
+    pinned staging buffers it allocates afterwards (first touch) and the threads that fill them
+    sit next to that GPU's PCIe root port.  With one serving process per GPU this keeps H2D
+    copies off the inter-socket link.  Returns the node, or -1 if nothing was changed."""
+    import os
+    node = C.c_int(-1)
+    _lib.check(_lib.load().drs_device_numa_node(int(device), C.byref(node)))
+    if node.value < 0:
+        return -1
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node.value) as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return -1
+        os.sched_setaffinity(0, cpus)
+    except (OSError, ValueError):
+        return -1
+    return node.value
+
+
 def pinned_empty(shape, dtype):
     """numpy array over cudaHostAlloc'ed memory (kept alive by the returned owner)."""
     lib = _lib.load()

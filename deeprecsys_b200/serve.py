@@ -22,6 +22,7 @@ from __future__ import absolute_import, division, print_function
 import json
 import multiprocessing as mp
 import sys
+import threading
 import time
 
 import numpy as np
@@ -52,71 +53,102 @@ def _sleep_until(t):
             return
         if dt > 0.002:
             time.sleep(dt - 0.001)      # coarse sleep, then spin (loadGenerator.py:57-64 does the same)
+        else:
+            time.sleep(0)               # yield the GIL: the Queue feeder thread must get to run,
+                                        # or a put() sits behind this spin for a switch interval
+
+
+class SystemHarness(object):
+    """One accel engine process (started once: dataset + parameters are regenerated inside it,
+    like every engine process of the reference) driven through the reference's Queue protocol;
+    ``run`` performs one experiment at a fixed mean inter-arrival time."""
+
+    def __init__(self, args):
+        self.args = args
+        ctx = mp.get_context("fork")        # DeepRecSys.py uses the default (fork) start method
+        self.accel_q = ctx.Queue(maxsize=32)                  # DeepRecSys.py:45
+        self.resp_q, self.ready_q = ctx.Queue(), ctx.Queue()
+        self.proc = ctx.Process(target=accelInferenceEngine,
+                                args=(args, self.accel_q, 0, self.resp_q, self.ready_q))
+        self.proc.daemon = True
+        self.proc.start()
+        self.ready_q.get()                                    # loadGenerator.py:76-78
+        self.responses = []
+        self.collector = threading.Thread(target=self._collect, daemon=True)
+        self.collector.start()
+        sys.setswitchinterval(1e-4)     # generator, Queue feeder and collector share one GIL
+
+    def _collect(self):
+        while True:
+            r = self.resp_q.get()
+            if r is None:
+                return
+            self.responses.append(r)
+
+    def run(self, n_queries, arrival_ms, seed=0, warmup_queries=20):
+        args = self.args
+        rng = np.random.RandomState(seed)
+        n_total = n_queries + warmup_queries
+        sizes = query_sizes(args, n_total, rng)
+        gaps = rng.exponential(arrival_ms / 1000.0, n_total)
+        first = len(self.responses)
+        t_next = time.time()
+        t_first = None
+        for i in range(n_total):
+            t_next += gaps[i]
+            _sleep_until(t_next)
+            req = ServiceRequest(batch_id=i % max(1, args.num_batches),
+                                 epoch=i // max(1, args.num_batches),
+                                 batch_size=int(sizes[i]), sub_id=0, total_sub_batches=1,
+                                 exp_packet=(i < warmup_queries))
+            req.arrival_time = time.time()
+            if i == warmup_queries:
+                t_first = req.arrival_time
+            self.accel_q.put(req)       # blocks when the engine falls behind (bounded queue)
+        deadline = time.time() + 120
+        while len(self.responses) - first < n_total and time.time() < deadline:
+            time.sleep(0.001)
+        got = self.responses[first:]
+        meas = [r for r in got if not r.exp_packet]
+        lat = np.array([r.inference_end_time - r.arrival_time for r in meas]) * 1e3
+        items = int(sum(r.batch_size for r in meas))
+        failed = sum(1 for r in meas if r.out_batch_size != r.batch_size)
+        span = max(r.inference_end_time for r in meas) - t_first
+        return {
+            "arrival_ms": arrival_ms, "queries": len(meas), "failed": failed, "items": items,
+            "offered_qps": 1000.0 / arrival_ms, "qps": len(meas) / span,
+            "inferences_per_s": items / span,
+            "p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)),
+            "p99_ms": float(np.percentile(lat, 99)), "max_ms": float(lat.max()),
+            "mean_query_size": float(np.mean([r.batch_size for r in meas])),
+        }
+
+    def close(self):
+        self.accel_q.put(None)
+        self.collector.join(timeout=120)
+        self.proc.join(timeout=60)
+        if self.proc.is_alive():
+            self.proc.terminate()
 
 
 def run_system(args, n_queries, arrival_ms, seed=0, warmup_queries=20):
     """One experiment at a fixed mean inter-arrival time.  Returns a dict of stats."""
-    ctx = mp.get_context("fork")        # DeepRecSys.py uses the default (fork) start method
-    accel_q = ctx.Queue(maxsize=32)     # DeepRecSys.py:45
-    resp_q, ready_q = ctx.Queue(), ctx.Queue()
-    proc = ctx.Process(target=accelInferenceEngine, args=(args, accel_q, 0, resp_q, ready_q))
-    proc.daemon = True
-    proc.start()
-    ready_q.get()                       # loadGenerator.py:76-78
-
-    rng = np.random.RandomState(seed)
-    n_total = n_queries + warmup_queries
-    sizes = query_sizes(args, n_total, rng)
-    gaps = rng.exponential(arrival_ms / 1000.0, n_total)
-    responses = []
-
-    import threading
-
-    def collect():
-        while True:
-            r = resp_q.get()
-            if r is None:
-                return
-            responses.append(r)
-
-    th = threading.Thread(target=collect, daemon=True)
-    th.start()
-    t_next = time.time()
-    t_first = None
-    for i in range(n_total):
-        t_next += gaps[i]
-        _sleep_until(t_next)
-        req = ServiceRequest(batch_id=i % max(1, args.num_batches), epoch=i // max(1, args.num_batches),
-                             batch_size=int(sizes[i]), sub_id=0, total_sub_batches=1,
-                             exp_packet=(i < warmup_queries))
-        req.arrival_time = time.time()
-        if i == warmup_queries:
-            t_first = req.arrival_time
-        accel_q.put(req)                # blocks when the engine falls behind (bounded queue)
-    accel_q.put(None)
-    th.join(timeout=120)
-    proc.join(timeout=60)
-
-    meas = [r for r in responses if not r.exp_packet]
-    lat = np.array([r.inference_end_time - r.arrival_time for r in meas]) * 1e3
-    items = int(sum(r.batch_size for r in meas))
-    failed = sum(1 for r in meas if r.out_batch_size != r.batch_size)
-    span = max(r.inference_end_time for r in meas) - t_first
-    return {
-        "arrival_ms": arrival_ms, "queries": len(meas), "failed": failed, "items": items,
-        "offered_qps": 1000.0 / arrival_ms, "qps": len(meas) / span,
-        "inferences_per_s": items / span,
-        "p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)),
-        "p99_ms": float(np.percentile(lat, 99)), "max_ms": float(lat.max()),
-        "mean_query_size": float(np.mean([r.batch_size for r in meas])),
-    }
+    h = SystemHarness(args)
+    try:
+        return h.run(n_queries, arrival_ms, seed=seed, warmup_queries=warmup_queries)
+    finally:
+        h.close()
 
 
 def sweep(args, rates_ms, n_queries, target_p99_ms=None):
-    """Run the experiment at each mean inter-arrival time; report the best
-    throughput whose p99 meets ``target_p99_ms`` (args.target_latency by default)."""
+    """Run the experiment at each mean inter-arrival time against ONE engine process; report
+    the best throughput whose p99 meets ``target_p99_ms`` (args.target_latency by default)."""
     target = float(target_p99_ms if target_p99_ms is not None else args.target_latency)
-    rows = [run_system(args, n_queries, r, seed=17 + i) for i, r in enumerate(rates_ms)]
+    h = SystemHarness(args)
+    try:
+        rows = [h.run(n_queries, r, seed=17 + i) for i, r in enumerate(rates_ms)]
+    finally:
+        h.close()
     ok = [r for r in rows if r["p99_ms"] <= target and r["failed"] == 0]
     best = max(ok, key=lambda r: r["inferences_per_s"]) if ok else None
     return {"target_p99_ms": target, "runs": rows, "best": best}

@@ -111,6 +111,10 @@ typedef struct {
 const char* drs_last_error(void);
 int drs_abi_version(void);
 int drs_device_count(int* n_out);
+/* NUMA node of the host bridge GPU `device` hangs off (from its PCI bus id via sysfs), or -1 when
+ * the platform does not say.  Serving processes bind themselves (CPU affinity + first-touch of
+ * their pinned staging buffers) to that node so that H2D copies do not cross sockets. */
+int drs_device_numa_node(int device, int* node_out);
 
 /* lifecycle */
 int drs_create(const drs_spec* spec, int device, drs_engine** out);

@@ -23,7 +23,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
-    for name in ("dlrm_cat", "wnd", "ncf", "din_many", "dlrm_rm3_like"):
+    for name in ("dlrm_cat", "wnd", "ncf", "din_many", "dlrm_rm3_like", "mtwnd"):
         mb = 24 if name == "dlrm_rm3_like" else 96
         c = make_case(name, num_batches=2, max_batch=mb)       # same seed on every rank
         S = shard.slice_size(mb, world)

@@ -17,12 +17,12 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
-def test_table_sharded_two_gpus_matches_oracle(precision):
+@pytest.mark.parametrize("world,precision", [(2, "fp32"), (2, "tf32x3"), (4, "tf32x3"),
+                                             (8, "fp32"), (8, "tf32x3")])
+def test_table_sharded_matches_oracle(world, precision):
     n = _ngpu()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs (have %d)" % n)
-    world = 2
+    if n < world:
+        pytest.skip("needs >= %d GPUs (have %d)" % (world, n))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29631",
            os.path.join(ROOT, "tests", "_shard_worker.py"), precision]

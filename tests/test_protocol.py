@@ -135,6 +135,23 @@ def test_real_backend_fails_loudly_without_gpu_or_library(monkeypatch):
         accel_mod.AccelBackend(args)
 
 
+def test_serving_harness_reports_latency_percentiles(monkeypatch):
+    """deeprecsys_b200.serve drives the engine through the same Queue protocol with Poisson
+    arrivals; here against the oracle-backed fake (no GPU in this tier)."""
+    from deeprecsys_b200 import serve
+    from oracle.cpu_inference_engine import OracleBackend
+    monkeypatch.setattr(accel_mod, "BACKEND_FACTORY", OracleBackend)
+    args = cli(SMALL_SYSTEM + ["--batch_size_distribution", "normal", "--avg_mini_batch_size", "20",
+                               "--var_mini_batch_size", "6", "--model_accel", "--queue"])
+    res = serve.sweep(args, [2.0, 1.0], 60, target_p99_ms=1000.0)
+    assert len(res["runs"]) == 2
+    for r in res["runs"]:
+        assert r["queries"] == 60 and r["failed"] == 0
+        assert r["p50_ms"] <= r["p95_ms"] <= r["p99_ms"] <= r["max_ms"]
+        assert 1 <= r["mean_query_size"] <= 64 and r["inferences_per_s"] > 0
+    assert res["best"] is not None
+
+
 # ------------------------------------------------------------------ tier 2
 SHIM_ACCEL = """
 from deeprecsys_b200 import accelInferenceEngine as _m
