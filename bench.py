@@ -54,9 +54,11 @@ def parse_args():
     p.add_argument("--precision", type=str, default="tf32x3",
                    help="MLP arithmetic: fp32 (FFMA) | tf32x3 (tcgen05, fp32-class) | tf32")
     p.add_argument("--lanes", type=int, default=3)
-    p.add_argument("--shard", type=str, default="replica", choices=["replica", "table"],
+    p.add_argument("--shard", type=str, default="replica", choices=["replica", "table", "row"],
                    help="N>1: replica (every rank all tables, own queries) | table (table-wise "
-                        "sharding, pooled vectors exchanged by K1's peer stores over NVLink)")
+                        "sharding, pooled vectors exchanged by K1's peer stores over NVLink) | "
+                        "row (row-wise sharding: every rank a row slice of every table, partial "
+                        "pooled vectors exchanged the same way and added at the owner)")
     p.add_argument("--interaction", type=str, default=None, help="override: cat | dot")
     p.add_argument("--cpu_seconds", type=float, default=10.0)
     p.add_argument("--cpu_sample", type=int, default=4096)
@@ -251,17 +253,19 @@ def run_b200(opts):
     numa_node = bind_to_device_numa_node(local) if world > 1 else -1
 
     B, nb = int(opts.batch), int(opts.staged_batches)        # B = samples per GPU per step
-    sharded = (world > 1 and opts.shard == "table")
+    sharded = (world > 1 and opts.shard in ("table", "row"))
+    row_mode = sharded and opts.shard == "row"
     GB = B * world if sharded else B                           # samples in one enqueued query
     a = model_args(opts, GB, nb)
     spec = ModelSpec(a)
     eng = AccelEngine(args=a, device=local, max_batch=B, precision=opts.precision,
-                      lanes=opts.lanes, max_lookups_per_table=GB * max(1, spec.L))
+                      lanes=opts.lanes, max_lookups_per_table=GB * max(1, spec.L),
+                      shard_mode="row" if row_mode else "table", shard_world=world)
     if sharded:
         shardlib.connect(eng, dist)
     keep_host = (rank == 0 and world == 1 and not opts.no_cpu_baseline)
     host_tables = []
-    only = set(shardlib.owned_tables(spec.T, rank, world)) if sharded else None
+    only = set(shardlib.owned_tables(spec.T, rank, world)) if (sharded and not row_mode) else None
     # replica: every rank has its own table contents and queries; table: one global model
     tseed = opts.seed if sharded else opts.seed + 1000 * rank
     for t, W in synth_tables(spec, tseed, only):
@@ -332,7 +336,8 @@ def run_b200(opts):
     gather_ms_avg = gather_ms / max(1, n_prof)
     # per launch: this rank's tables x the query's samples (table mode: T/world tables x B*world
     # samples = the same bytes as replica mode's T tables x B samples when T % world == 0)
-    own_frac = (len(only) / float(spec.T)) if sharded else 1.0
+    # (row mode: all T tables, ~1/world of every sample's lookups)
+    own_frac = (1.0 / world) if row_mode else (len(only) / float(spec.T)) if sharded else 1.0
     bytes_per_launch = bytes_per_sample * GB * own_frac
     traffic, traffic_src = load_traffic(opts, spec, B, sharded)
     # One gather launch per step.  With >= 3 lanes consecutive gather launches overlap each other
@@ -515,8 +520,8 @@ def run_b200(opts):
                                                      spec.table_rows[0], spec.D, spec.L, B,
                                                      max(1, B // 1024)),
                        "global_batch": B * world,
-                       "parallelism": ("table-sharded x%d (K1 peer stores over NVLink)" % world
-                                       if sharded else "replica x%d" % world),
+                       "parallelism": ("%s-sharded x%d (K1 peer stores over NVLink)"
+                                       % (opts.shard, world) if sharded else "replica x%d" % world),
                        "l2_policy": "inputs larger than L2 (4.1 GB tables, uniform ids; "
                                     "%d staged batches cycled)" % nb,
                        "mlp_precision": opts.precision, "lanes": opts.lanes,

@@ -23,6 +23,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cctype>
 #include <chrono>
 #include <cstdarg>
@@ -38,6 +39,7 @@
 #include "mlp_ffma.cuh"
 #include "mlp_chain.cuh"
 #include "mlp_tc.cuh"
+#include "rowshard.cuh"
 #include "shard.cuh"
 #include "sls_gather.cuh"
 
@@ -106,6 +108,12 @@ struct InputSet {                 // one query's inputs in HBM
   int32_t* lengths = nullptr;     // [T, n]
   int32_t* off = nullptr;         // [T, n+1]
   int64_t* idx64 = nullptr;       // scratch for int64 uploads
+  // row-sharded mode: the uploaded query (global ids) before bucketing by this rank's row range
+  int32_t* idx_raw = nullptr;     // same slab layout as idx
+  int32_t* lengths_raw = nullptr; // [T, n]
+  int32_t* off_raw = nullptr;     // [T, n+1]
+  ScanTableDesc* scan_raw = nullptr;   // [T] device
+  RowBucketDesc* bdescs = nullptr;     // [T] device
   SlsTableDesc* descs = nullptr;  // [T_owned] device (gather descriptors of the owned tables)
   ScanTableDesc* scan = nullptr;  // [T] device
   std::vector<int64_t> idx_pos;   // per table start (ints, multiple of 4)
@@ -180,6 +188,9 @@ struct drs_engine {
   size_t lane_G_off[kMaxLanes] = {0, 0, 0, 0};
   size_t flags_off = 0;       // uint32 [lanes][2][kMaxShardRanks]: arrived, consumed
   int rank = 0, world = 1;
+  bool row_mode = false;      // spec.shard_mode == DRS_SHARD_ROW
+  size_t lane_part_off[kMaxLanes] = {0, 0, 0, 0};   // row mode: partial slab [world][max_batch][T*D]
+  std::vector<int64_t> row0, row1;                   // row mode: this rank's row range per table
   unsigned char* peer_slab[kMaxShardRanks] = {nullptr};
   std::vector<int> owned;     // tables owned by this rank (all tables when world == 1)
 
@@ -258,12 +269,22 @@ int alloc_input_set(drs_engine* e, InputSet& s, int n, int dense_rows,
   TRY(dev_alloc_t(e, &s.off, (size_t)T * (n + 1)));
   TRY(dev_alloc_t(e, &s.descs, (size_t)T));
   TRY(dev_alloc_t(e, &s.scan, (size_t)T));
+  if (e->row_mode) {
+    TRY(dev_alloc_t(e, &s.idx_raw, (size_t)pos + 4));
+    CU(cudaMemsetAsync(s.idx_raw, 0, ((size_t)pos + 4) * sizeof(int32_t), stream));
+    TRY(dev_alloc_t(e, &s.lengths_raw, (size_t)T * n));
+    TRY(dev_alloc_t(e, &s.off_raw, (size_t)T * (n + 1)));
+    TRY(dev_alloc_t(e, &s.scan_raw, (size_t)T));
+    TRY(dev_alloc_t(e, &s.bdescs, (size_t)T));
+  }
   return DRS_OK;
 }
 
 void free_input_set(InputSet& s) {
   cudaFree(s.dense); cudaFree(s.idx); cudaFree(s.idx64); cudaFree(s.lengths);
   cudaFree(s.off); cudaFree(s.descs); cudaFree(s.scan);
+  cudaFree(s.idx_raw); cudaFree(s.lengths_raw); cudaFree(s.off_raw); cudaFree(s.scan_raw);
+  cudaFree(s.bdescs);
   s = InputSet();
 }
 
@@ -274,26 +295,50 @@ int gather_dst_col(const drs_engine* e, int t) {
   return t * e->D;                                         // P = [e_0 .. e_{T-1}]
 }
 
-bool owns(const drs_engine* e, int t) { return e->world == 1 || (t % e->world) == e->rank; }
+bool owns(const drs_engine* e, int t) {
+  return e->world == 1 || e->row_mode || (t % e->world) == e->rank;
+}
 
 int write_descs(drs_engine* e, InputSet& s, const std::vector<int64_t>& n_idx,
                 cudaStream_t stream) {
   std::vector<SlsTableDesc> d;
-  std::vector<ScanTableDesc> sc(e->T);
+  std::vector<ScanTableDesc> sc(e->T), sc_raw(e->T);
+  std::vector<RowBucketDesc> bd(e->T);
+  const bool row = e->row_mode && e->world > 1;
   for (int t = 0; t < e->T; ++t) {
     if (owns(e, t)) {
       SlsTableDesc x{};
       x.rows = e->tables[t];
       x.idx = s.idx + s.idx_pos[t];
       x.off = s.off + (size_t)t * (s.n + 1);
-      x.n_rows = e->table_rows[t];
-      x.dst_col = gather_dst_col(e, t);
+      x.n_rows = row ? e->row1[t] - e->row0[t] : e->table_rows[t];
+      x.dst_col = row ? t * e->D : gather_dst_col(e, t);   // row mode: partial layout [T*D]
       x.pad_ = t;
       d.push_back(x);
     }
     sc[t].lengths = s.lengths + (size_t)t * s.n;
     sc[t].off = s.off + (size_t)t * (s.n + 1);
-    sc[t].n_idx = n_idx.empty() ? -1 : n_idx[t];
+    sc[t].n_idx = (n_idx.empty() || row) ? -1 : n_idx[t];
+    if (row) {
+      sc_raw[t].lengths = s.lengths_raw + (size_t)t * s.n;
+      sc_raw[t].off = s.off_raw + (size_t)t * (s.n + 1);
+      sc_raw[t].n_idx = n_idx.empty() ? -1 : n_idx[t];
+      RowBucketDesc& b = bd[t];
+      b.idx_raw = s.idx_raw + s.idx_pos[t];
+      b.off_raw = sc_raw[t].off;
+      b.len_local = s.lengths + (size_t)t * s.n;
+      b.off_local = sc[t].off;
+      b.idx_local = s.idx + s.idx_pos[t];
+      b.n_rows = e->table_rows[t];
+      b.row0 = (int32_t)e->row0[t];
+      b.row1 = (int32_t)e->row1[t];
+    }
+  }
+  if (row) {
+    CU(cudaMemcpyAsync(s.scan_raw, sc_raw.data(), sc_raw.size() * sizeof(ScanTableDesc),
+                       cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(s.bdescs, bd.data(), bd.size() * sizeof(RowBucketDesc),
+                       cudaMemcpyHostToDevice, stream));
   }
   if (!d.empty())
     CU(cudaMemcpyAsync(s.descs, d.data(), d.size() * sizeof(SlsTableDesc), cudaMemcpyHostToDevice,
@@ -489,8 +534,18 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
   if (e->world > 1) {
     p.shard_S = ceil_div(B, e->world);
     const int li = (int)(&ln - e->lanes);
-    for (int q = 0; q < e->world; ++q)
-      p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_G_off[li]);
+    if (e->row_mode) {
+      // partial pooled vectors -> owner's partial slab, block `rank` of [world][max_batch][T*D]
+      const int64_t TD = (int64_t)e->T * e->D;
+      p.ld_out = TD;
+      p.vec_store = (e->D % 4 == 0) ? 1 : 0;
+      for (int q = 0; q < e->world; ++q)
+        p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_part_off[li]) +
+                        (int64_t)e->rank * e->spec.max_batch * TD;
+    } else {
+      for (int q = 0; q < e->world; ++q)
+        p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_G_off[li]);
+    }
   }
   if (p.T == 0) return DRS_OK;
   int grid = ceil_div(B, e->SB);
@@ -511,7 +566,19 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
   return launch_gather_lpr<false>(e, ln.stream, p, e->lpr, grid, e->sls_smem);
 }
 
+// lengths -> offsets for the first B samples of `s`.  Row-sharded mode: offsets of the raw
+// (global-id) segments, bucket the ids by this rank's row range, offsets of the local segments.
 int launch_scan(drs_engine* e, cudaStream_t st, const InputSet& s, int B, int* d_err) {
+  if (e->row_mode && e->world > 1) {
+    const int grid = ceil_div(e->T * B * kWarp, kBucketThreads);
+    k_lengths_to_offsets<<<e->T, kScanThreads, 0, st>>>(s.scan_raw, B, d_err);
+    k_row_bucket<false><<<grid, kBucketThreads, 0, st>>>(s.bdescs, e->T, B, d_err);
+    k_lengths_to_offsets<<<e->T, kScanThreads, 0, st>>>(s.scan, B, d_err);
+    k_row_bucket<true><<<grid, kBucketThreads, 0, st>>>(s.bdescs, e->T, B, d_err);
+    CU(cudaGetLastError());
+    e->launches += 4;
+    return DRS_OK;
+  }
   k_lengths_to_offsets<<<e->T, kScanThreads, 0, st>>>(s.scan, B, d_err);
   CU(cudaGetLastError());
   e->launches += 1;
@@ -556,6 +623,25 @@ int shard_wait(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
   k_shard_wait<<<1, 32, 0, ln.stream>>>(flag_ptr(e, e->rank, li, which), e->world, epoch, ln.d_err);
   CU(cudaGetLastError());
   e->launches += 1;
+  return DRS_OK;
+}
+
+// After K1 on a sharded engine: publish "my peer stores are issued", wait for every peer's, and
+// in row mode add the world partial pooled vectors of this rank's samples (rank order) into the
+// gather-output buffer the interaction / MLP kernels read.
+int exchange_after_gather(drs_engine* e, Lane& ln, int rows) {
+  if (e->world <= 1) return DRS_OK;
+  TRY(shard_signal(e, ln, 0, ln.epoch));
+  TRY(shard_wait(e, ln, 0, ln.epoch));
+  if (e->row_mode && rows > 0) {
+    const int li = (int)(&ln - e->lanes);
+    const int TD = e->T * e->D;
+    const float* partial = reinterpret_cast<const float*>(e->slab + e->lane_part_off[li]);
+    k_row_reduce<<<ew_grid((int64_t)rows * TD), 256, 0, ln.stream>>>(
+        partial, e->world, e->spec.max_batch, TD, rows, ln.G, e->ld_G, gather_dst_col(e, 0));
+    CU(cudaGetLastError());
+    e->launches += 1;
+  }
   return DRS_OK;
 }
 
@@ -604,10 +690,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, ln, s, B, e->dot));
       PROF_MARK(2);
-      if (e->world > 1) {
-        TRY(shard_signal(e, ln, 0, ln.epoch));
-        TRY(shard_wait(e, ln, 0, ln.epoch));
-      }
+      TRY(exchange_after_gather(e, ln, rows));
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
@@ -621,10 +704,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      if (e->world > 1) {
-        TRY(shard_signal(e, ln, 0, ln.epoch));
-        TRY(shard_wait(e, ln, 0, ln.epoch));
-      }
+      TRY(exchange_after_gather(e, ln, rows));
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
@@ -640,10 +720,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      if (e->world > 1) {
-        TRY(shard_signal(e, ln, 0, ln.epoch));
-        TRY(shard_wait(e, ln, 0, ln.epoch));
-      }
+      TRY(exchange_after_gather(e, ln, rows));
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       if (rows > 0) {
         const int nl = (int)e->task.layers.size();
@@ -667,10 +744,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      if (e->world > 1) {
-        TRY(shard_signal(e, ln, 0, ln.epoch));
-        TRY(shard_wait(e, ln, 0, ln.epoch));
-      }
+      TRY(exchange_after_gather(e, ln, rows));
       if (rows > 0) {
         k_add_cols<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(ln.P, ln.P + D, ldp, ln.F,
                                                                       ldf, rows, D);
@@ -687,10 +761,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       PROF_MARK(1);
       TRY(launch_gather(e, ln, s, B, false));
       PROF_MARK(2);
-      if (e->world > 1) {
-        TRY(shard_signal(e, ln, 0, ln.epoch));
-        TRY(shard_wait(e, ln, 0, ln.epoch));
-      }
+      TRY(exchange_after_gather(e, ln, rows));
       if (rows > 0) {
         k_din_concat<<<ew_grid((int64_t)nu * rows * D), 256, 0, ln.stream>>>(
             ln.P, ldp, ln.C, cap * 3 * D, rows, D, nu, T - 2);
@@ -785,6 +856,9 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
     CU(cudaMemcpyAsync(s.dense, dense, (size_t)B * e->m_den * sizeof(float),
                        cudaMemcpyHostToDevice, stream));
   }
+  const bool row = e->row_mode && e->world > 1;
+  int32_t* const dst_idx = row ? s.idx_raw : s.idx;         // row mode: bucketed later on the GPU
+  int32_t* const dst_len = row ? s.lengths_raw : s.lengths;
   std::vector<int64_t>& n_idx = *n_idx_out;
   n_idx.assign(T, 0);
   for (int t = 0; t < T; ++t) {
@@ -804,23 +878,23 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
   for (int t = 1; t < T && len_strided; ++t)
     len_strided = ((const char*)lengths[t] - (const char*)lengths[t - 1]) == lstride;
   if (len_strided && lstride >= (ptrdiff_t)(B * sizeof(int32_t)) && B > 0) {
-    CU(cudaMemcpy2DAsync(s.lengths, (size_t)s.n * sizeof(int32_t), lengths[0], (size_t)lstride,
+    CU(cudaMemcpy2DAsync(dst_len, (size_t)s.n * sizeof(int32_t), lengths[0], (size_t)lstride,
                          (size_t)B * sizeof(int32_t), T, cudaMemcpyHostToDevice, stream));
   } else {
     for (int t = 0; t < T; ++t)
-      CU(cudaMemcpyAsync(s.lengths + (size_t)t * s.n, lengths[t], (size_t)B * sizeof(int32_t),
+      CU(cudaMemcpyAsync(dst_len + (size_t)t * s.n, lengths[t], (size_t)B * sizeof(int32_t),
                          cudaMemcpyHostToDevice, stream));
   }
   const size_t isz = idx_is_i64 ? sizeof(int64_t) : sizeof(int32_t);
   // ids: equal counts + equal host stride + equal device stride -> one 2-D copy
-  bool idx_strided = T > 1 && !idx_is_i64 && e->world == 1;
+  bool idx_strided = T > 1 && !idx_is_i64 && (e->world == 1 || row);
   const ptrdiff_t istride = T > 1 ? (const char*)idx[1] - (const char*)idx[0] : 0;
   const int64_t dstride = T > 1 ? s.idx_pos[1] - s.idx_pos[0] : 0;
   for (int t = 1; t < T && idx_strided; ++t)
     idx_strided = ((const char*)idx[t] - (const char*)idx[t - 1]) == istride &&
                   (s.idx_pos[t] - s.idx_pos[t - 1]) == dstride && n_idx[t] == n_idx[0];
   if (idx_strided && n_idx[0] > 0 && istride >= (ptrdiff_t)(n_idx[0] * isz)) {
-    CU(cudaMemcpy2DAsync(s.idx + s.idx_pos[0], (size_t)dstride * sizeof(int32_t), idx[0],
+    CU(cudaMemcpy2DAsync(dst_idx + s.idx_pos[0], (size_t)dstride * sizeof(int32_t), idx[0],
                          (size_t)istride, (size_t)n_idx[0] * sizeof(int32_t), T,
                          cudaMemcpyHostToDevice, stream));
   } else {
@@ -830,11 +904,11 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
         CU(cudaMemcpyAsync(s.idx64 + s.idx_pos[t], idx[t], (size_t)n_idx[t] * sizeof(int64_t),
                            cudaMemcpyHostToDevice, stream));
         k_cast_i64_i32<<<ew_grid(n_idx[t]), 256, 0, stream>>>(s.idx64 + s.idx_pos[t],
-                                                              s.idx + s.idx_pos[t], n_idx[t]);
+                                                              dst_idx + s.idx_pos[t], n_idx[t]);
         CU(cudaGetLastError());
         e->launches += 1;
       } else {
-        CU(cudaMemcpyAsync(s.idx + s.idx_pos[t], idx[t], (size_t)n_idx[t] * sizeof(int32_t),
+        CU(cudaMemcpyAsync(dst_idx + s.idx_pos[t], idx[t], (size_t)n_idx[t] * sizeof(int32_t),
                            cudaMemcpyHostToDevice, stream));
       }
     }
@@ -905,6 +979,11 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
             "unknown precision %d", spec->precision);
   CHECK_ARG(spec->n_lanes >= 0 && spec->n_lanes <= kMaxLanes, "n_lanes must be in [0,%d]",
             kMaxLanes);
+  CHECK_ARG(spec->shard_mode == DRS_SHARD_TABLE || spec->shard_mode == DRS_SHARD_ROW,
+            "unknown shard_mode %d", spec->shard_mode);
+  CHECK_ARG(spec->shard_mode != DRS_SHARD_ROW ||
+                (spec->shard_world >= 2 && spec->shard_world <= kMaxShardRanks),
+            "row-wise sharding needs shard_world in [2,%d]", kMaxShardRanks);
   for (int t = 0; t < spec->n_tables; ++t)
     CHECK_ARG(spec->table_rows[t] >= 1 && spec->table_rows[t] < (int64_t(1) << 31),
               "table %d: rows must be in [1, 2^31) (ids are int32 after the Cast)", t);
@@ -922,6 +1001,7 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
     const char* g = getenv("DRS_GATHER_CTAS_PER_SM");
     if (g) e->gather_ctas_per_sm = atoi(g);
   }
+  e->row_mode = spec->shard_mode == DRS_SHARD_ROW;
   e->T = spec->n_tables;
   e->D = spec->emb_dim;
   e->n_lanes = spec->n_lanes > 0 ? spec->n_lanes : 2;
@@ -1045,6 +1125,12 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
     for (int i = 0; i < e->n_lanes; ++i) { e->lane_G_off[i] = off; off += g_bytes; }
     e->flags_off = off;
     off += (size_t)kMaxLanes * 2 * kMaxShardRanks * sizeof(uint32_t);
+    off = (off + 255) & ~size_t(255);
+    if (e->row_mode) {   // partial pooled vectors written by the peers: [world][max_batch][T*D]
+      const size_t p_bytes =
+          (((size_t)spec->shard_world * maxB * T * D * sizeof(float)) + 255) & ~size_t(255);
+      for (int i = 0; i < e->n_lanes; ++i) { e->lane_part_off[i] = off; off += p_bytes; }
+    }
     e->slab_bytes = (off + 255) & ~size_t(255);
     TRYB(dev_alloc(e, (void**)&e->slab, e->slab_bytes));
     CUB(cudaMemset(e->slab, 0, e->slab_bytes));
@@ -1145,12 +1231,20 @@ int drs_load_table(drs_engine* e, int table, const float* rows, int64_t n_rows, 
             (long long)e->table_rows[table], e->D);
   CU(cudaSetDevice(e->device));
   TRY(sync_all(e));
+  int64_t first = 0, count = n_rows;            // row mode: keep only this rank's slice
+  if (e->row_mode) {
+    if (e->world <= 1)
+      return fail(DRS_ERR_STATE, "row-sharded engine: drs_shard_connect before drs_load_table");
+    first = e->row0[table];
+    count = e->row1[table] - e->row0[table];
+  }
   if (!e->tables[table]) {
     // +16 floats of slack keeps 16-B vector loads of the last row in-bounds for any D
-    TRY(dev_alloc_t(e, &e->tables[table], (size_t)n_rows * dim + 16));
+    TRY(dev_alloc_t(e, &e->tables[table], (size_t)count * dim + 16));
   }
-  CU(cudaMemcpyAsync(e->tables[table], rows, (size_t)n_rows * dim * sizeof(float),
-                     cudaMemcpyHostToDevice, s0(e)));
+  if (count > 0)
+    CU(cudaMemcpyAsync(e->tables[table], rows + first * dim, (size_t)count * dim * sizeof(float),
+                       cudaMemcpyHostToDevice, s0(e)));
   CU(cudaStreamSynchronize(s0(e)));
   e->table_loaded[table] = 1;
   return rewrite_all_descs(e);       // descriptors hold the table pointers
@@ -1410,6 +1504,9 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
   CHECK_ARG(table >= 0 && table < e->T, "table %d out of range", table);
   CHECK_ARG(n_segments >= 0 && n_idx >= 0, "negative sizes");
   if (!e->table_loaded[table]) return fail(DRS_ERR_STATE, "table %d not loaded", table);
+  if (e->row_mode)
+    return fail(DRS_ERR_STATE, "the operator entry needs a whole table; this engine is "
+                               "row-sharded (every rank holds a row slice)");
   if (n_segments == 0) return DRS_OK;
   CU(cudaSetDevice(e->device));
   Lane& ln = e->lanes[0];
@@ -1540,6 +1637,20 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
     case DRS_STAGE_OUT:
       src = ln.out; c = e->out_dim; ld = c;
       break;
+    case DRS_STAGE_IDS: {
+      CHECK_ARG(layer >= 0 && layer < T && owns(e, layer), "table %d not gathered on this rank",
+                layer);
+      const InputSet& in = *ln.last_inputs;
+      int32_t n_ids = 0;
+      CU(cudaMemcpy(&n_ids, in.off + (size_t)layer * (in.n + 1) + ln.last_B, sizeof(int32_t),
+                    cudaMemcpyDeviceToHost));
+      r = 1; c = n_ids;
+      CHECK_ARG((int64_t)c <= cap, "capacity too small: need %d floats", c);
+      if (c > 0)
+        CU(cudaMemcpy(dst, in.idx + in.idx_pos[layer], (size_t)c * 4, cudaMemcpyDeviceToHost));
+      *rows = r; *cols = c;
+      return DRS_OK;
+    }
     case DRS_STAGE_OFFSETS: {
       r = T; c = ln.last_B + 1;
       CHECK_ARG((int64_t)r * c <= cap, "capacity too small: need %lld floats", (long long)r * c);
@@ -1636,6 +1747,11 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
   CHECK_ARG(!(e->dot), "table-sharded mode does not support the fused dot interaction "
                        "(it needs every table of a sample in one CTA); use replica mode");
   CHECK_ARG(e->world == 1, "already connected");
+  CHECK_ARG(!e->row_mode || world == e->spec.shard_world,
+            "row-sharded engine was created for %d ranks, connect says %d", e->spec.shard_world,
+            world);
+  for (int t = 0; t < e->T && e->row_mode; ++t)
+    CHECK_ARG(!e->table_loaded[t], "row-sharded engine: connect before loading tables");
   CU(cudaSetDevice(e->device));
   TRY(sync_all(e));
   const unsigned char* blobs = static_cast<const unsigned char*>(all_blobs);
@@ -1654,6 +1770,15 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
   }
   e->rank = rank;
   e->world = world;
+  if (e->row_mode) {
+    e->row0.assign(e->T, 0);
+    e->row1.assign(e->T, 0);
+    for (int t = 0; t < e->T; ++t) {
+      const int64_t n = e->table_rows[t], chunk = ceil_div64(n, world);
+      e->row0[t] = std::min(n, (int64_t)rank * chunk);
+      e->row1[t] = std::min(n, e->row0[t] + chunk);
+    }
+  }
   e->owned.clear();
   for (int t = 0; t < e->T; ++t) if (owns(e, t)) e->owned.push_back(t);
   {  // tile geometry follows the number of tables this rank gathers

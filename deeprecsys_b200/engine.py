@@ -30,7 +30,7 @@ def _ptr_array(arrays):
 
 class AccelEngine(object):
     def __init__(self, args=None, spec=None, device=0, max_batch=None, precision=None,
-                 lanes=0, max_lookups_per_table=None):
+                 lanes=0, max_lookups_per_table=None, shard_mode="table", shard_world=1):
         self.lib = _lib.load()
         self.spec = spec if spec is not None else ModelSpec(args)
         s = self.spec
@@ -56,8 +56,14 @@ class AccelEngine(object):
         cs.interaction_itself = int(s.interaction_itself)
         cs.max_batch = self.max_batch
         cs.max_lookups_per_table = int(max_lookups_per_table or self.max_batch * max(1, s.L))
+        self._max_lookups = cs.max_lookups_per_table
         cs.precision = _lib.PRECISIONS[precision]
         cs.n_lanes = int(lanes)
+        if shard_mode not in ("table", "row"):
+            raise ValueError("shard_mode must be 'table' or 'row'")
+        self.shard_mode = shard_mode
+        cs.shard_mode = _lib.SHARD_ROW if shard_mode == "row" else _lib.SHARD_TABLE
+        cs.shard_world = int(shard_world) if shard_mode == "row" else 0
         if s.model_type == "mtwnd":
             self._task = (C.c_int32 * len(s.ln_task))(*s.ln_task)
             cs.n_tasks, cs.n_task, cs.ln_task = s.n_tasks, len(s.ln_task), self._task
@@ -230,13 +236,15 @@ class AccelEngine(object):
     def fetch_stage(self, stage, layer=0):
         cap = self.max_batch * max(self.spec.T * self.spec.D, max(self.spec.ln_top),
                                    max(self.spec.ln_bot or [1]), self.max_batch + 1) + 16
+        if stage == _lib.STAGE_IDS:
+            cap = max(cap, int(self._max_lookups) + 16)
         buf = np.empty(cap, dtype=np.float32)
         rows, cols = C.c_int(), C.c_int()
         _lib.check(self.lib.drs_fetch_stage(self._handle, int(stage), int(layer), _ptr(buf), cap,
                                             C.byref(rows), C.byref(cols)))
         n = rows.value * cols.value
         view = buf[:n].reshape(rows.value, cols.value)
-        if stage == _lib.STAGE_OFFSETS:
+        if stage in (_lib.STAGE_OFFSETS, _lib.STAGE_IDS):
             return view.view(np.int32).copy()
         return view.copy()
 

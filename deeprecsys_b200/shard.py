@@ -9,8 +9,15 @@ table    table-wise sharding: table t lives on rank t % world; for a
          buffer through peer-mapped memory (the C library does that;
          torch.distributed is only the rendezvous that carries the IPC handles).
 
-The integer bucketing here mirrors csrc/engine.cu exactly (owns(),
-enqueue_graph()) and is what the gloo tests check.
+row      row-wise sharding: rank r holds rows [r*chunk, min(N, (r+1)*chunk)),
+         chunk = ceil(N / world), of EVERY table.  Each rank buckets the query's ids
+         by its row range (order kept, rebased to the slice), gathers partial pooled
+         vectors for all B samples into the owner rank's partial slab, and the owner
+         adds the world partials in rank order.  Useful when T < world (DIN: 4 tables)
+         or one table outgrows a GPU; reassociates the fp32 sum (not bit-exact).
+
+The integer bucketing here mirrors csrc/engine.cu / csrc/rowshard.cuh exactly (owns(),
+enqueue_graph(), k_row_bucket) and is what the gloo tests check.
 """
 from __future__ import absolute_import, division, print_function
 
@@ -21,6 +28,30 @@ def owned_tables(n_tables, rank, world):
 
 def table_owner(t, world):
     return 0 if world == 1 else t % world
+
+
+def row_range(n_rows, rank, world):
+    """[row0, row1) of a table's rows held by ``rank`` under row-wise sharding."""
+    n_rows, world = int(n_rows), int(world)
+    chunk = -(-n_rows // world)
+    row0 = min(n_rows, rank * chunk)
+    return row0, min(n_rows, row0 + chunk)
+
+
+def row_owner(row, n_rows, world):
+    return int(row) // (-(-int(n_rows) // int(world)))
+
+
+def bucket_rows(ids, lengths, row0, row1):
+    """Integer reference of k_row_bucket: keep, in order, the ids of every segment that fall
+    into [row0, row1), rebased to the slice.  -> (local_ids int32, local_lengths int32)."""
+    import numpy as np
+    ids = np.asarray(ids).astype(np.int64)
+    lengths = np.asarray(lengths).astype(np.int64)
+    mine = (ids >= row0) & (ids < row1)
+    seg = np.repeat(np.arange(lengths.shape[0]), lengths)
+    local_len = np.bincount(seg[mine], minlength=lengths.shape[0]).astype(np.int32)
+    return (ids[mine] - row0).astype(np.int32), local_len
 
 
 def slice_size(batch, world):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRS_ABI_VERSION 2
+#define DRS_ABI_VERSION 3
 
 /* status codes */
 enum {
@@ -52,6 +52,11 @@ enum { DRS_INTERACT_CAT = 0, DRS_INTERACT_DOT = 1 };
  * (fp32-class accuracy); TF32 = tcgen05 single pass (throughput mode). */
 enum { DRS_PREC_FP32 = 0, DRS_PREC_TF32X3 = 1, DRS_PREC_TF32 = 2 };
 
+/* multi-GPU sharding of the embedding tables (one process per GPU).
+ * TABLE: table t lives on rank t % world.  ROW: every table is split by rows, rank r holds rows
+ * [r*chunk, min(N, (r+1)*chunk)), chunk = ceil(N / world). */
+enum { DRS_SHARD_TABLE = 0, DRS_SHARD_ROW = 1 };
+
 /* mlp ids for drs_load_fc */
 enum {
   DRS_MLP_BOT = 0,         /* DLRM bottom MLP (dlrm_s_caffe2.py:376)                        */
@@ -69,7 +74,9 @@ enum {
   DRS_STAGE_TOP = 3,       /* layer k output of the top MLP                  */
   DRS_STAGE_OUT = 4,       /* final output [B, out_dim]                      */
   DRS_STAGE_OFFSETS = 5,   /* int32 offsets [T, B+1] reinterpret as float bits (bit-exact bucketing check) */
-  DRS_STAGE_TASK = 6       /* MT-WnD: layer (task * 256 + k) = output of layer k of task head `task` */
+  DRS_STAGE_TASK = 6,      /* MT-WnD: layer (task * 256 + k) = output of layer k of task head `task` */
+  DRS_STAGE_IDS = 7        /* int32 ids the gather reads for table `layer` ([1, n] as float bits); row-sharded
+                              mode: this rank's bucketed, rebased ids (bit-exact bucketing check) */
 };
 
 typedef struct drs_engine drs_engine;
@@ -98,6 +105,9 @@ typedef struct {
   const int32_t* ln_task;        /* arch_mlp_tasks; ln_task[0] == ln_top[n_top-1]            */
   int32_t task_sigmoid_layer;    /* 1-based task layer that gets Sigmoid (the reference passes
                                     sigmoid_top = len(ln_top) - 1 to every head), 0 = none    */
+  /* multi-GPU (zero = single GPU or table-wise sharding decided at drs_shard_connect) */
+  int32_t shard_mode;            /* DRS_SHARD_*; ROW must be declared here (sizes the partial slab) */
+  int32_t shard_world;           /* ROW: number of ranks (2..8)                              */
 } drs_spec;
 
 /* per-call timing, milliseconds */
@@ -201,7 +211,15 @@ int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms
 int drs_host_alloc(void** ptr, int64_t bytes);
 int drs_host_free(void* ptr);
 
-/* Multi-GPU, one process per GPU (table-wise sharding).
+/* Multi-GPU, one process per GPU.
+ * Row-wise sharding (spec.shard_mode = DRS_SHARD_ROW): connect first, then drs_load_table with
+ * the FULL table (the rank keeps only its row slice).  Per query every rank buckets the ids by
+ * its row range on the GPU (integer-exact, order-preserving), gathers PARTIAL pooled vectors for
+ * all samples and stores them into the owner rank's partial slab; the owner adds the `world`
+ * partials in rank order.  The fp32 sum is therefore reassociated relative to one GPU
+ * (rtol 1e-6), while table-wise sharding below stays bit-exact.
+ *
+ * Table-wise sharding (default):
  * Each rank owns tables {t : t % world == rank}; after the gather every rank
  * holds all T pooled vectors for its slice of the query's samples.  The
  * exchange is done by the gather kernel itself storing pooled rows straight

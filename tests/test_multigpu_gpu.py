@@ -30,3 +30,19 @@ def test_table_sharded_matches_oracle(world, precision):
                           text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-4000:]
     assert proc.stdout.count("DONE") == world, proc.stdout[-4000:]
+
+
+@pytest.mark.parametrize("world,precision", [(2, "fp32"), (4, "tf32x3"), (8, "fp32")])
+def test_row_sharded_matches_oracle(world, precision):
+    """Row-wise sharding (every rank a row slice of every table): integer-exact bucketing,
+    pooled vectors bit-exact vs the rank-order emulation, outputs vs the oracle."""
+    n = _ngpu()
+    if n < world:
+        pytest.skip("needs >= %d GPUs (have %d)" % (world, n))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29641",
+           os.path.join(ROOT, "tests", "_shard_worker.py"), precision, "row"]
+    proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-4000:]
+    assert proc.stdout.count("DONE") == world, proc.stdout[-4000:]

@@ -33,6 +33,50 @@ def test_bucketing_is_a_partition():
     assert [len(shard.owned_tables(10, r, 8)) for r in range(8)] == [2, 2, 1, 1, 1, 1, 1, 1]
 
 
+def test_row_ranges_partition_every_table():
+    for world in (2, 3, 4, 8):
+        for n in (1, 5, 8, 9, 1000, 4000000, 28000):
+            ranges = [shard.row_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+                assert a1 == b0 and a0 <= a1
+            for r, (r0, r1) in enumerate(ranges):
+                for row in {r0, r1 - 1} if r1 > r0 else ():
+                    assert shard.row_owner(row, n, world) == r
+
+
+def test_row_bucketing_is_order_preserving_and_lossless():
+    """Integer reference of csrc/rowshard.cuh's k_row_bucket (the GPU is compared against this
+    bit-for-bit in tests/_shard_worker.py): the per-rank buckets partition every segment's ids,
+    keep their order and rebase them to the rank's slice."""
+    from oracle import numpy_oracle as O
+    rng = np.random.RandomState(5)
+    n_rows, world = 1003, 4
+    lengths = rng.randint(0, 30, size=41).astype(np.int32)
+    lengths[7] = 0
+    ids = rng.randint(0, n_rows, size=int(lengths.sum()))
+    seg = np.repeat(np.arange(lengths.shape[0]), lengths)
+    total = np.zeros_like(lengths)
+    for r in range(world):
+        row0, row1 = shard.row_range(n_rows, r, world)
+        lid, llen = shard.bucket_rows(ids, lengths, row0, row1)
+        assert lid.dtype == np.int32 and llen.dtype == np.int32
+        assert lid.size == llen.sum() and (lid >= 0).all() and (lid < row1 - row0).all()
+        total += llen
+        pos = 0
+        for b, k in enumerate(llen):                  # original order, rebased to the slice
+            want = [v - row0 for v in ids[seg == b] if row0 <= v < row1]
+            assert lid[pos:pos + k].tolist() == want
+            pos += k
+    assert np.array_equal(total, lengths)             # every id lands in exactly one bucket
+    # and the row-wise pooled sum equals the sequential one up to fp32 reassociation
+    W = rng.uniform(-1, 1, (n_rows, 8)).astype(np.float32)
+    a = O.sparse_lengths_sum(W, ids, lengths)
+    b = O.sparse_lengths_sum_rowwise(W, ids, lengths, world)
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(O.sparse_lengths_sum_rowwise(W, ids, lengths, 1), a)
+
+
 class _FakeEngine(object):
     def __init__(self, rank):
         self.rank = rank
