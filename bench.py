@@ -476,7 +476,7 @@ def run_b200(opts):
     # accelInferenceEngine as a separate process behind the reference's Queue protocol, Poisson
     # arrivals, query sizes normal(256, 32) clipped to [1, 1024] (run_DeepRecInfra.sh:34-37).
     system, res = None, None
-    if rank == 0 and world == 1 and not opts.no_system and opts.config == "rm1":
+    if not opts.no_system and opts.config == "rm1" and not sharded:
         # a fresh interpreter: the harness forks the engine process (as DeepRecSys.py does), and
         # a forked child cannot use CUDA once its parent — this process — has initialised it
         cfg = os.path.join(ROOT, "deeprecsys_b200", "models", "configs", CONFIGS[opts.config])
@@ -484,7 +484,8 @@ def run_b200(opts):
                "--num_batches", "32", "--max_mini_batch_size", "1024",
                "--batch_size_distribution", "normal", "--avg_mini_batch_size", "256",
                "--var_mini_batch_size", "32", "--model_accel", "--queue",
-               "--numpy_rand_seed", str(opts.seed), "--accel_precision", opts.precision,
+               "--numpy_rand_seed", str(opts.seed + rank), "--accel_precision", opts.precision,
+               "--accel_device", str(local),
                "--serve_rates_ms", opts.system_rates_ms,
                "--serve_queries", str(opts.system_queries)]
         try:
@@ -494,12 +495,29 @@ def run_b200(opts):
             res = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
         except Exception as exc:            # the serving leg must not cost the bench line
             system = {"error": repr(exc)}
-    if res:
+    if dist is not None and not opts.no_system and opts.config == "rm1" and not sharded:
+        # N > 1: one (load generator, engine process) pair per GPU, run side by side; the job's
+        # figure is the sum of the pairs' throughputs at the largest of their p99s
+        allres = [None] * world
+        dist.all_gather_object(allres, res)
+        if rank == 0 and all(r and r["best"] for r in allres):
+            bests = [r["best"] for r in allres]
+            res = {"target_p99_ms": allres[0]["target_p99_ms"], "runs": [r["runs"] for r in allres],
+                   "best": {"inferences_per_s": sum(b["inferences_per_s"] for b in bests),
+                            "qps": sum(b["qps"] for b in bests),
+                            "p99_ms": max(b["p99_ms"] for b in bests),
+                            "p95_ms": max(b["p95_ms"] for b in bests)}}
+        elif rank == 0:
+            res = None
+            system = {"error": "a rank's serving run failed or missed the p99 target"}
+    if res and rank == 0:
         best = res["best"]
         system = {"what": "accelInferenceEngine process behind multiprocessing Queues "
                           "(ServiceRequest in, ServiceResponse out), Poisson arrivals, query "
                           "sizes normal(256,32) in [1,1024], 32 pre-generated batches; latency = "
-                          "inference_end_time - arrival_time (DeepRecSys.py:122-123)",
+                          "inference_end_time - arrival_time (DeepRecSys.py:122-123); one "
+                          "generator + engine pair per GPU",
+                  "pairs": world,
                   "target_p99_ms": res["target_p99_ms"],
                   "inferences_per_s_at_p99": best["inferences_per_s"] if best else None,
                   "qps": best["qps"] if best else None,

@@ -506,7 +506,9 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
   const int groups = lpr > 0 ? kSlsThreads / lpr : kSlsThreads / kWarp;
   int SB = groups / (T > 0 ? T : 1);
   if (SB < 1) SB = 1;
-  if (SB > 16) SB = 16;
+  // one segment per lane group and round: with few tables per rank (table-sharded RMC1 on 8
+  // GPUs gathers ONE table) a tile must carry up to `groups` samples or lane groups sit idle
+  if (SB > 64) SB = 64;
   int idx_cap = 0;
   if (avg_len >= 8) {
     int64_t want = ((int64_t)SB * avg_len + 3 + 3) & ~int64_t(3);

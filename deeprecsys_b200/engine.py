@@ -201,6 +201,14 @@ class AccelEngine(object):
                                               out_ptr, C.byref(t)))
         return t.value
 
+    def submit_host(self, dense_ptr, ids_ptrs, is64, len_ptrs, batch_size, out_ptr=None):
+        """Asynchronous serve of a query held in (pinned) host buffers: H2D, kernels and D2H are
+        enqueued on the next lane; returns a ticket for ``wait``.  Raw pointers, no numpy work."""
+        t = C.c_int64()
+        _lib.check(self.lib.drs_submit_host(self._handle, dense_ptr, ids_ptrs, int(is64), len_ptrs,
+                                            int(batch_size), out_ptr, C.byref(t)))
+        return t.value
+
     def wait(self, ticket):
         _lib.check(self.lib.drs_wait(self._handle, int(ticket)))
 
