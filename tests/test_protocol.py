@@ -135,15 +135,30 @@ def test_real_backend_fails_loudly_without_gpu_or_library(monkeypatch):
         accel_mod.AccelBackend(args)
 
 
-def test_serving_harness_reports_latency_percentiles(monkeypatch):
+HARNESS_SCRIPT = """
+import json, sys
+from deeprecsys_b200 import accelInferenceEngine as accel_mod, serve
+from deeprecsys_b200.utils.utils import cli
+from oracle.cpu_inference_engine import OracleBackend
+accel_mod.BACKEND_FACTORY = OracleBackend          # CPU test tier only: no GPU here
+args = cli(%r)
+print(json.dumps(serve.sweep(args, [2.0, 1.0], 60, target_p99_ms=1000.0)))
+"""
+
+
+def test_serving_harness_reports_latency_percentiles():
     """deeprecsys_b200.serve drives the engine through the same Queue protocol with Poisson
-    arrivals; here against the oracle-backed fake (no GPU in this tier)."""
-    from deeprecsys_b200 import serve
-    from oracle.cpu_inference_engine import OracleBackend
-    monkeypatch.setattr(accel_mod, "BACKEND_FACTORY", OracleBackend)
-    args = cli(SMALL_SYSTEM + ["--batch_size_distribution", "normal", "--avg_mini_batch_size", "20",
-                               "--var_mini_batch_size", "6", "--model_accel", "--queue"])
-    res = serve.sweep(args, [2.0, 1.0], 60, target_p99_ms=1000.0)
+    arrivals; here against the oracle-backed fake (no GPU in this tier).  Run in a fresh
+    interpreter: the harness forks the engine process, and a child forked from this
+    (multi-threaded, torch-using) pytest process can deadlock in torch's thread pool."""
+    import json
+    argv = SMALL_SYSTEM + ["--batch_size_distribution", "normal", "--avg_mini_batch_size", "20",
+                           "--var_mini_batch_size", "6", "--model_accel", "--queue"]
+    proc = subprocess.run([sys.executable, "-c", HARNESS_SCRIPT % (argv,)], cwd=ROOT,
+                          env=dict(os.environ, PYTHONPATH=ROOT, PYTHONWARNINGS="ignore"),
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    res = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
     assert len(res["runs"]) == 2
     for r in res["runs"]:
         assert r["queries"] == 60 and r["failed"] == 0
