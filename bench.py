@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     "rm1": "dlrm_rm1.json", "rm2": "dlrm_rm2.json", "rm3": "dlrm_rm3.json",
     "wnd": "wide_and_deep.json", "ncf": "ncf.json", "din": "din.json",
+    "dien": "dien.json", "mtwnd": "mtwnd.json",
 }
 METRIC = "DLRM-RMC1 inferences/sec"
 UNIT = "inferences/s"
@@ -107,6 +108,14 @@ def synth_fcs(spec, seed):
     for mlp_id, ln in spec.mlps:
         for layer in range(len(ln) - 1):
             fcs[(mlp_id, layer)] = draw_fc(ln[layer], ln[layer + 1])
+    if spec.model_type == "dien":       # recurrent cells: XavierFill-distributed, zero biases
+        from deeprecsys_b200._lib import MLP_RNN_BASE
+        for cell, (n_in, H) in enumerate(spec.rnn):
+            for layer, fan_in in ((0, n_in), (1, H)):
+                sc = np.sqrt(3.0 / fan_in)
+                fcs[(MLP_RNN_BASE + cell, layer)] = (
+                    np.random.uniform(-sc, sc, size=(H, fan_in)).astype(np.float32),
+                    np.zeros(H, np.float32))
     return fcs
 
 

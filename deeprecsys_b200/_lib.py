@@ -13,19 +13,19 @@ from . import build as _build
 
 # enums of drs_b200.h
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_COMM = range(6)
-MODEL_DLRM, MODEL_WND, MODEL_NCF, MODEL_DIN, MODEL_MTWND = range(5)
+MODEL_DLRM, MODEL_WND, MODEL_NCF, MODEL_DIN, MODEL_MTWND, MODEL_DIEN = range(6)
 INTERACT_CAT, INTERACT_DOT = 0, 1
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
-MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE = 0, 1, 2, 16, 4096
+MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE, MLP_RNN_BASE = 0, 1, 2, 16, 4096, 8192
 (STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS, STAGE_TASK,
  STAGE_IDS) = range(8)
 SHARD_TABLE, SHARD_ROW = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 SHARD_BLOB_BYTES = 192
 
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
 MODEL_TYPES = {"dlrm": MODEL_DLRM, "wnd": MODEL_WND, "ncf": MODEL_NCF, "din": MODEL_DIN,
-               "mtwnd": MODEL_MTWND}
+               "mtwnd": MODEL_MTWND, "dien": MODEL_DIEN}
 
 
 class DrsError(RuntimeError):
@@ -45,6 +45,7 @@ class Spec(C.Structure):
         ("precision", C.c_int32), ("n_lanes", C.c_int32),
         ("n_tasks", C.c_int32), ("n_task", C.c_int32), ("ln_task", C.POINTER(C.c_int32)),
         ("task_sigmoid_layer", C.c_int32),
+        ("hidden_size", C.c_int32),
         ("shard_mode", C.c_int32), ("shard_world", C.c_int32),
     ]
 

@@ -44,9 +44,8 @@ except ImportError:                    # standalone
     from deeprecsys_b200.utils.packets import ServiceResponse
     from deeprecsys_b200.utils.utils import debugPrint
 
-# the reference's whitelist (accelInferenceEngine.py:37) plus ncf, minus the one
-# graph that is not on the accel path yet (dien: SURVEY 8f)
-SUPPORTED_MODEL_NAMES = ("wnd", "rm1", "rm2", "rm3", "din", "ncf", "mtwnd")
+# the reference's whitelist (accelInferenceEngine.py:37) plus ncf
+SUPPORTED_MODEL_NAMES = ("wnd", "rm1", "rm2", "rm3", "din", "dien", "mtwnd", "ncf")
 
 
 class AccelBackend(object):

@@ -39,6 +39,7 @@
 #include "mlp_ffma.cuh"
 #include "mlp_chain.cuh"
 #include "mlp_tc.cuh"
+#include "rnn.cuh"
 #include "rowshard.cuh"
 #include "shard.cuh"
 #include "sls_gather.cuh"
@@ -136,6 +137,9 @@ struct Lane {
   float* C = nullptr;             // DIN: [n_units, cap_rows, 3D]
   std::vector<float*> ybot, ytop, yfin;   // per-layer outputs
   std::vector<float*> ytask;              // MT-WnD: per-layer outputs [n_tasks, cap, width]
+  float* seq = nullptr;                   // DIEN: sequence input [N*cap, D]
+  float* rnn_pre = nullptr;               // DIEN: i2h term of all steps [N*cap, H]
+  float* rnn_h0 = nullptr;                // DIEN: hidden states of cell 0 [N*cap, H]
   float* out = nullptr;
   int* d_err = nullptr;
   int* h_err = nullptr;           // pinned
@@ -158,6 +162,8 @@ struct drs_engine {
   std::vector<char> table_loaded;
   Mlp bot, top, fin;          // DIN: bot = attention MLP batched over n_units
   Mlp task;                   // MT-WnD: task heads batched over n_tasks (own weights each)
+  Mlp rnn[2];                 // DIEN: cell l = {layer 0: i2h FC [H, in], layer 1: gates_t FC [H, H]}
+  int H = 0, n_steps = 0;     // DIEN: hidden size, sequence length N = T - 3
   std::vector<int32_t> ln_task;
 
   int n_lanes = 2;
@@ -656,6 +662,8 @@ int check_ready(drs_engine* e) {
   if (!e->top.all_loaded()) return fail(DRS_ERR_STATE, "top MLP weights not loaded");
   if (!e->fin.all_loaded()) return fail(DRS_ERR_STATE, "final FC weights not loaded");
   if (!e->task.all_loaded()) return fail(DRS_ERR_STATE, "task-head MLP weights not loaded");
+  if (!e->rnn[0].all_loaded() || !e->rnn[1].all_loaded())
+    return fail(DRS_ERR_STATE, "recurrent cell weights not loaded");
   return DRS_OK;
 }
 
@@ -738,6 +746,46 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
           in = y; ld_in = ldy; bs_in = bsy; rows_in = (int64_t)nt * cap;
         }
       }
+      break;
+    }
+    case DRS_MODEL_DIEN: {
+      // dien.py:386-433 (single GPU only: the reference's Reshape mixes samples across the batch)
+      const int64_t ldp = (int64_t)T * D;
+      const int N = e->n_steps, H = e->H;
+      PROF_MARK(1);
+      TRY(launch_gather(e, ln, s, B, false));
+      PROF_MARK(2);
+      if (rows > 0) {
+        k_dien_seq<<<ew_grid((int64_t)N * rows * D), 256, 0, ln.stream>>>(ln.P, ldp, ln.seq, rows,
+                                                                          N, D);
+        CU(cudaGetLastError());
+        e->launches += 1;
+        const int64_t seq_rows = (int64_t)N * cap;
+        const int rnn_grid = ceil_div(rows, kRnnRows);
+        const size_t rnn_smem = rnn_smem_bytes(H);
+        // cell 0: i2h over all N steps at once, then the recurrence
+        TRY(launch_fc(e, ln, e->rnn[0].layers[0], ln.seq, D, 0, seq_rows, ln.rnn_pre, H, 0,
+                      N * rows));
+        k_rnn_tanh<<<rnn_grid, kRnnThreads, rnn_smem, ln.stream>>>(
+            ln.rnn_pre, e->rnn[0].layers[1].W, e->rnn[0].layers[1].b, N, rows, H, ln.rnn_h0,
+            nullptr, 0);
+        // cell 1 reads every hidden state of cell 0; only its last state is used (dien.py:380)
+        TRY(launch_fc(e, ln, e->rnn[1].layers[0], ln.rnn_h0, H, 0, seq_rows, ln.rnn_pre, H, 0,
+                      N * rows));
+        k_rnn_tanh<<<rnn_grid, kRnnThreads, rnn_smem, ln.stream>>>(
+            ln.rnn_pre, e->rnn[1].layers[1].W, e->rnn[1].layers[1].b, N, rows, H, nullptr, ln.R,
+            e->ld_R);
+        CU(cudaGetLastError());
+        e->launches += 2;
+        const int cols[3] = {0, T - 2, T - 1};       // profile, candidate ad, context (dien.py:418-420)
+        for (int k = 0; k < 3; ++k) {
+          k_copy_cols<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(
+              ln.P + (int64_t)cols[k] * D, ldp, ln.R + H + k * D, e->ld_R, rows, D);
+          CU(cudaGetLastError());
+          e->launches += 1;
+        }
+      }
+      TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
     case DRS_MODEL_NCF: {
@@ -1090,6 +1138,46 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
         e->task.layers[spec->task_sigmoid_layer - 1].act = kActSigmoid;
       break;
     }
+    case DRS_MODEL_DIEN: {
+      CHECKB(T >= 4, "DIEN needs at least 4 embedding tables");          // dien.py:457
+      CHECKB(spec->hidden_size >= 1 && spec->hidden_size <= kRnnMaxH,
+             "DIEN hidden_size must be in [1,%d]", kRnnMaxH);
+      e->H = spec->hidden_size;
+      e->n_steps = T - 3;
+      CHECKB(e->ln_top[0] == e->H + 3 * D, "DIEN top mlp input must be hidden_size + 3*D");
+      e->m_den = 0;
+      e->ld_R = e->H + 3 * D;
+      TRYB(alloc_mlp_params(e, e->top, e->ln_top, 1, kActRelu));
+      {
+        std::vector<int32_t> c0 = {D, e->H}, cg = {e->H, e->H};
+        for (int l = 0; l < 2; ++l) {
+          // two independent FCs per cell, stored as "layers" 0 (i2h) and 1 (gates_t)
+          Mlp& m = e->rnn[l];
+          m.layers.resize(2);
+          for (int k = 0; k < 2; ++k) {
+            Layer& y = m.layers[k];
+            y.in = (k == 0) ? (l == 0 ? D : e->H) : e->H;
+            y.out = e->H;
+            y.n_units = 1;
+            y.act = kActNone;
+            y.loaded.assign(1, 0);
+            TRYB(dev_alloc_t(e, &y.W, (size_t)y.out * y.in));
+            TRYB(dev_alloc_t(e, &y.b, (size_t)y.out));
+            if (k == 0 && e->spec.precision != DRS_PREC_FP32)
+              TRYB(dev_alloc_t(e, &y.Wsplit, (size_t)2 * y.out * y.in));
+          }
+        }
+      }
+      {
+        static bool attr_set = false;
+        if (!attr_set) {
+          CUB(cudaFuncSetAttribute(k_rnn_tanh, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)rnn_smem_bytes(kRnnMaxH)));
+          attr_set = true;
+        }
+      }
+      break;
+    }
     case DRS_MODEL_NCF: {
       CHECKB(T == 4, "NCF only has 4 embedding tables");                 // ncf.py:352
       CHECKB(e->ln_top.size() >= 3 && e->ln_top[0] == 2 * D, "NCF top mlp input must be 2*D");
@@ -1154,6 +1242,11 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
       TRYB(dev_alloc_t(e, &ln.F, (size_t)maxB * (D + tower_out)));
     if (spec->model_type == DRS_MODEL_DIN)
       TRYB(dev_alloc_t(e, &ln.C, (size_t)e->n_units * maxB * 3 * D));
+    if (spec->model_type == DRS_MODEL_DIEN) {
+      TRYB(dev_alloc_t(e, &ln.seq, (size_t)e->n_steps * maxB * D));
+      TRYB(dev_alloc_t(e, &ln.rnn_pre, (size_t)e->n_steps * maxB * e->H));
+      TRYB(dev_alloc_t(e, &ln.rnn_h0, (size_t)e->n_steps * maxB * e->H));
+    }
     TRYB(alloc_mlp_acts(e, e->bot, ln.ybot));
     TRYB(alloc_mlp_acts(e, e->top, ln.ytop));
     TRYB(alloc_mlp_acts(e, e->fin, ln.yfin));
@@ -1196,7 +1289,7 @@ int drs_destroy(drs_engine* e) {
   for (int q = 0; q < e->world; ++q)
     if (q != e->rank && e->peer_slab[q]) cudaIpcCloseMemHandle(e->peer_slab[q]);
   for (float* t : e->tables) cudaFree(t);
-  for (Mlp* m : {&e->bot, &e->top, &e->fin, &e->task})
+  for (Mlp* m : {&e->bot, &e->top, &e->fin, &e->task, &e->rnn[0], &e->rnn[1]})
     for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wsplit); }
   for (auto& kv : e->staged) free_input_set(kv.second);
   for (int i = 0; i < kMaxLanes; ++i) {
@@ -1204,6 +1297,7 @@ int drs_destroy(drs_engine* e) {
     if (!e->gather_into_R) cudaFree(ln.R);
     if (e->dot) cudaFree(ln.P);
     cudaFree(ln.dense_out); cudaFree(ln.F); cudaFree(ln.C);
+    cudaFree(ln.seq); cudaFree(ln.rnn_pre); cudaFree(ln.rnn_h0);
     for (auto* v : {&ln.ybot, &ln.ytop, &ln.yfin, &ln.ytask}) for (float* p : *v) cudaFree(p);
     free_input_set(ln.slot);
     cudaFree(ln.d_err);
@@ -1270,6 +1364,10 @@ int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const floa
            mlp_id - DRS_MLP_TASK_BASE < e->spec.n_tasks) {
     m = &e->task;
     unit = mlp_id - DRS_MLP_TASK_BASE;
+  }
+  else if (mlp_id >= DRS_MLP_RNN_BASE && mlp_id < DRS_MLP_RNN_BASE + 2 &&
+           e->spec.model_type == DRS_MODEL_DIEN) {
+    m = &e->rnn[mlp_id - DRS_MLP_RNN_BASE];
   }
   CHECK_ARG(m != nullptr, "mlp_id %d does not exist in this model", mlp_id);
   CHECK_ARG(layer >= 0 && layer < (int)m->layers.size(), "layer %d out of range [0,%d)", layer,
@@ -1594,6 +1692,7 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
       break;
     case DRS_STAGE_BOT: {
       if (e->spec.model_type == DRS_MODEL_DIN) { src = ln.R + D; ld = e->ld_R; c = D; break; }
+      if (e->spec.model_type == DRS_MODEL_DIEN) { src = ln.R; ld = e->ld_R; c = e->H; break; }  // last hidden state
       CHECK_ARG(e->spec.model_type == DRS_MODEL_DLRM, "model has no bottom MLP");
       CHECK_ARG(layer >= 0 && layer < (int)e->bot.layers.size(), "bottom layer out of range");
       const Layer& l = e->bot.layers[layer];
@@ -1746,6 +1845,9 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
   CHECK_ARG(e && all_blobs, "NULL argument");
   CHECK_ARG(world >= 1 && world <= kMaxShardRanks && rank >= 0 && rank < world,
             "rank %d / world %d out of range (max %d ranks)", rank, world, kMaxShardRanks);
+  CHECK_ARG(e->spec.model_type != DRS_MODEL_DIEN,
+            "DIEN cannot be sharded by samples: the reference's Reshape of the behaviour "
+            "embeddings (dien.py:303-305) mixes samples across the whole batch; use replicas");
   CHECK_ARG(!(e->dot), "table-sharded mode does not support the fused dot interaction "
                        "(it needs every table of a sample in one CTA); use replica mode");
   CHECK_ARG(e->world == 1, "already connected");

@@ -59,6 +59,7 @@ class AccelEngine(object):
         self._max_lookups = cs.max_lookups_per_table
         cs.precision = _lib.PRECISIONS[precision]
         cs.n_lanes = int(lanes)
+        cs.hidden_size = int(getattr(s, "hidden_size", 0))
         if shard_mode not in ("table", "row"):
             raise ValueError("shard_mode must be 'table' or 'row'")
         self.shard_mode = shard_mode

@@ -10,6 +10,14 @@ Dimension rules per model (reference file:line):
         final FC = [D + top[-2], top[-1]].
   din   models/din.py:246-258,346-359    attention MLP = [3D] + arch_mlp_bot + [D]
         per behaviour table (tables 1..T-3); top input = 4D.
+  dien  models/dien.py:296-433           table roles as DIN; the N = T-3 behaviour embeddings
+        feed two stacked tanh BasicRNN cells (D -> H, H -> H, H = --hidden_size); the last hidden
+        state is concatenated with profile / candidate-ad / context embeddings -> top MLP
+        [H + 3D] + arch_mlp_top, all ReLU.  The cells' weights are re-initialised by Caffe2's own
+        XavierFill when the reference runs model.param_init_net (dien.py:502), so they do NOT
+        come from the numpy stream: the reference's numpy randn draws for them are consumed (to
+        keep the stream aligned for the top MLP) and XavierFill-distributed weights are drawn
+        from a private RandomState(numpy_rand_seed).
   mtwnd models/multi_task_wnd.py:304-316,340-362  WnD trunk with an all-ReLU shared top MLP,
         then num_multi_tasks heads of widths arch_mlp_tasks (own weights each); every head is
         built with sigmoid_layer = len(ln_top) - 1, i.e. the Sigmoid lands on task layer
@@ -79,6 +87,17 @@ class ModelSpec(object):
             tower = self.ln_top[:-1]
             self.mlps = [(_lib.MLP_TOP, tower), (_lib.MLP_FINAL, [D + tower[-1], self.ln_top[-1]])]
             self.sigmoid_last = False
+        elif self.model_type == "dien":
+            if T < 4:
+                raise ValueError("DIEN needs at least 4 embedding tables")        # dien.py:457
+            self.m_den, self.ln_bot = 0, []
+            self.hidden_size = int(args.hidden_size)
+            self.n_steps = T - 3
+            self.ln_top = [self.hidden_size + 3 * D] + arch_top                  # dien.py:426-429
+            self.rnn = [(D, self.hidden_size), (self.hidden_size, self.hidden_size)]
+            self.mlps = [(_lib.MLP_TOP, self.ln_top)]
+            self.sigmoid_last = False
+            self.seed = int(getattr(args, "numpy_rand_seed", 0))
         elif self.model_type == "mtwnd":
             if self.interaction_op != "cat" or len(arch_bot) != 1:
                 raise ValueError("multi-task wide&deep needs cat interaction and a single "
@@ -153,6 +172,18 @@ def iter_parameters(spec):
     one at a time."""
     for t, rows in enumerate(spec.table_rows):
         yield ("table", t, draw_table(rows, spec.D))
+    if spec.model_type == "dien":
+        # dien.py:307-310, 359-362: four randn draws per cell, fed and then overwritten by the
+        # framework's initialiser -> consume them, then draw XavierFill-distributed weights
+        # (U(+-sqrt(3 / fan_in)), zero biases) from a private stream.  Cell l is addressed as
+        # mlp id MLP_RNN_BASE + l with "layer" 0 = i2h, "layer" 1 = gates_t.
+        private = np.random.RandomState(spec.seed)
+        for cell, (n_in, H) in enumerate(spec.rnn):
+            np.random.randn(H, H); np.random.randn(H); np.random.randn(H, n_in); np.random.randn(H)
+            for layer, fan_in in ((0, n_in), (1, H)):
+                scale = np.sqrt(3.0 / fan_in)
+                W = private.uniform(-scale, scale, size=(H, fan_in)).astype(np.float32)
+                yield ("fc", _lib.MLP_RNN_BASE + cell, layer, W, np.zeros(H, np.float32))
     for mlp_id, ln in spec.mlps:
         for layer in range(len(ln) - 1):
             W, b = draw_fc(ln[layer], ln[layer + 1])

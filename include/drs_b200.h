@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRS_ABI_VERSION 3
+#define DRS_ABI_VERSION 4
 
 /* status codes */
 enum {
@@ -43,7 +43,7 @@ enum {
 /* model graphs (reference: models/dlrm_s_caffe2.py, wide_and_deep.py, ncf.py, din.py,
  * multi_task_wnd.py) */
 enum { DRS_MODEL_DLRM = 0, DRS_MODEL_WND = 1, DRS_MODEL_NCF = 2, DRS_MODEL_DIN = 3,
-       DRS_MODEL_MTWND = 4 };
+       DRS_MODEL_MTWND = 4, DRS_MODEL_DIEN = 5 /* models/dien.py */ };
 
 /* arch_interaction_op (dlrm_s_caffe2.py:334-365) */
 enum { DRS_INTERACT_CAT = 0, DRS_INTERACT_DOT = 1 };
@@ -63,13 +63,17 @@ enum {
   DRS_MLP_TOP = 1,         /* DLRM/WnD/DIN top MLP; NCF: the MLP tower ln_top[:-1] (ncf.py:332) */
   DRS_MLP_FINAL = 2,       /* NCF final FC over [Zmf, tower] (ncf.py:339-343)               */
   DRS_MLP_ATTN_BASE = 16,  /* DIN attention unit i -> DRS_MLP_ATTN_BASE + i (din.py:260-278) */
-  DRS_MLP_TASK_BASE = 4096 /* MT-WnD task head i -> DRS_MLP_TASK_BASE + i (multi_task_wnd.py:304-316) */
+  DRS_MLP_TASK_BASE = 4096,/* MT-WnD task head i -> DRS_MLP_TASK_BASE + i (multi_task_wnd.py:304-316) */
+  DRS_MLP_RNN_BASE = 8192  /* DIEN recurrent cell l (0, 1) -> DRS_MLP_RNN_BASE + l; its "layer" 0 is the
+                              input FC i2h [H, in], "layer" 1 the recurrent FC gates_t [H, H]
+                              (rnn_cell.BasicRNN as called at dien.py:318-328, 370-378) */
 };
 
 /* stage taps for drs_fetch_stage (stage-level parity) */
 enum {
   DRS_STAGE_POOLED = 0,    /* [B, T*D] pooled vectors, table-major columns   */
-  DRS_STAGE_BOT = 1,       /* layer k output of the bottom MLP [B, ln_bot[k+1]] (DIN: summed attention output, layer ignored) */
+  DRS_STAGE_BOT = 1,       /* layer k output of the bottom MLP [B, ln_bot[k+1]] (DIN: summed attention output,
+                              DIEN: last hidden state of the second recurrent cell [B, H]; layer ignored) */
   DRS_STAGE_INTERACT = 2,  /* top-MLP input [B, ln_top[0]]                   */
   DRS_STAGE_TOP = 3,       /* layer k output of the top MLP                  */
   DRS_STAGE_OUT = 4,       /* final output [B, out_dim]                      */
@@ -105,6 +109,7 @@ typedef struct {
   const int32_t* ln_task;        /* arch_mlp_tasks; ln_task[0] == ln_top[n_top-1]            */
   int32_t task_sigmoid_layer;    /* 1-based task layer that gets Sigmoid (the reference passes
                                     sigmoid_top = len(ln_top) - 1 to every head), 0 = none    */
+  int32_t hidden_size;           /* DIEN: width H of the two recurrent cells (--hidden_size)   */
   /* multi-GPU (zero = single GPU or table-wise sharding decided at drs_shard_connect) */
   int32_t shard_mode;            /* DRS_SHARD_*; ROW must be declared here (sizes the partial slab) */
   int32_t shard_world;           /* ROW: number of ranks (2..8)                              */

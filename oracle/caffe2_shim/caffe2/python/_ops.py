@@ -130,6 +130,44 @@ def op_Add(ins, outs, args):
     return [np.asarray(ins[0]) + np.asarray(ins[1])]
 
 
+# ---- parameter initialisers (brew / rnn_cell put these into model.param_init_net) -------------
+def op_XavierFill(ins, outs, args):
+    # Caffe2 XavierFill: U(-sqrt(3 / fan_in), +sqrt(3 / fan_in)), fan_in = size / dim0.
+    # Drawn from numpy's global RNG here (Caffe2 uses its own generator).
+    shape = tuple(int(v) for v in args["shape"])
+    fan_in = int(np.prod(shape)) // shape[0]
+    scale = np.sqrt(3.0 / fan_in)
+    return [np.random.uniform(-scale, scale, size=shape).astype(F32)]
+
+
+def op_ConstantFill(ins, outs, args):
+    shape = tuple(int(v) for v in args["shape"])
+    return [np.full(shape, args.get("value", 0.0), dtype=F32)]
+
+
+def op_BasicRNNShim(ins, outs, args):
+    # rnn_cell.BasicRNN(activation="tanh"), see caffe2/python/rnn_cell.py in this shim
+    x, seq_len, h0, wi, bi, wg, bg = (np.asarray(v) for v in ins)
+    x = x.astype(F32)
+    N, B, _ = x.shape
+    H = wg.shape[0]
+    h = h0.astype(F32).reshape(-1, H)[-B:] if h0.ndim == 3 else h0.astype(F32).reshape(B, H)
+    i2h = (x.reshape(N * B, -1) @ wi.T.astype(F32) + bi).astype(F32).reshape(N, B, H)
+    seq_len = np.asarray(seq_len).astype(np.int64).ravel()
+    all_h = np.zeros((N, B, H), dtype=F32)
+    for t in range(N):
+        gates = ((h @ wg.T.astype(F32)).astype(F32) + bg).astype(F32)     # FC(h_{t-1})
+        gates = (gates + i2h[t]).astype(F32)                               # Sum(gates_t, input_t)
+        h_new = np.tanh(gates).astype(F32)
+        valid = (seq_len > t)[:, None]
+        if int(args.get("drop_states", 0)):
+            h = np.where(valid, h_new, F32(0)).astype(F32)
+        else:
+            h = np.where(valid, h_new, h).astype(F32)
+        all_h[t] = h
+    return [all_h, h.reshape(1, B, H).copy()]
+
+
 # ---- blob queues (dlrm_s_caffe2.py:180-211, 257, 307-314) ----------------------------------
 def op_CreateBlobsQueue(ins, outs, args):
     import queue

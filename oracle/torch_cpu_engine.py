@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE = 0, 1, 2, 16, 4096
+MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE, MLP_RNN_BASE = 0, 1, 2, 16, 4096, 8192
 
 
 class TorchCpuModel(object):
@@ -82,6 +82,20 @@ class TorchCpuModel(object):
             heads = [self._mlp(shared, self._layers(MLP_TASK_BASE + k),
                                sigmoid_layer=s.task_sigmoid_layer) for k in range(s.n_tasks)]
             return torch.cat(heads, dim=1)
+        if s.model_type == "dien":
+            T, N = s.T, s.T - 3
+            x = torch.cat(pooled[1:T - 2], dim=1).reshape(N, -1, s.D)
+            for cell in range(2):
+                (wi, bi), (wg, bg) = self._layers(MLP_RNN_BASE + cell)
+                i2h = torch.addmm(bi, x.reshape(-1, x.shape[2]), wi.t()).reshape(N, -1, wg.shape[0])
+                h = torch.zeros(i2h.shape[1], wg.shape[0])
+                outs = []
+                for t in range(N):
+                    h = torch.tanh(torch.addmm(bg, h, wg.t()) + i2h[t])
+                    outs.append(h)
+                x = torch.stack(outs, dim=0)
+            R = torch.cat([x[-1], pooled[0], pooled[T - 2], pooled[T - 1]], dim=1)
+            return self._mlp(R, self._layers(MLP_TOP))
         if s.model_type == "ncf":
             zmf = pooled[0] + pooled[1]
             tower = self._mlp(torch.cat([pooled[2], pooled[3]], dim=1), self._layers(MLP_TOP))

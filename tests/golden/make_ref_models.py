@@ -49,6 +49,7 @@ WRAPPERS = {
     "ncf": (ref_engine.NCF_Wrapper, "ncf"),
     "din": (ref_engine.DIN_Wrapper, "din"),
     "mtwnd": (ref_engine.MT_Wide_and_Deep_Wrapper, "mtwnd"),
+    "dien": (ref_engine.DIEN_Wrapper, "dien"),
 }
 
 EXTRA = {}
@@ -126,6 +127,13 @@ def direct_flow(name, queue=True):
             net.run(lX[j], lS_l[j], lS_i[j])
             for k, v in activation_blobs(net.model.net).items():
                 res["%s/req_%d_%d/%s" % (tag, j, MAX_BATCH, k)] = v
+    if args.model_type == "dien":
+        # the recurrent cells' parameters come from param_init_net (XavierFill / ConstantFill,
+        # dien.py:318-380 via rnn_cell.BasicRNN), not from the numpy stream: record them
+        for scope in ("rnn_0", "rnn_1"):
+            for key in ("i2h_w", "i2h_b", "gates_t_w", "gates_t_b"):
+                res["%s/params/%s/%s" % (tag, scope, key)] = workspace.FetchBlob(
+                    "%s/%s" % (scope, key)).copy()
     res[tag + "/argv"] = np.array(argv)
     res[tag + "/op_types"] = np.array([op.type for op in net.model.net.ops])
     return res, args

@@ -54,6 +54,10 @@ SMALL = {
               "--arch_mlp_top", "64-32", "--arch_mlp_tasks", "32-16-1",
               "--arch_interaction_op", "cat", "--num_indices_per_lookup", "1",
               "--num_multi_tasks", "3"],
+    "dien": ["--model_type", "dien", "--arch_embedding_size",
+             "300-" + "-".join(["200"] * 5) + "-400-500", "--arch_sparse_feature_size", "16",
+             "--arch_mlp_bot", "24", "--arch_mlp_top", "40-20-2", "--arch_interaction_op", "cat",
+             "--num_indices_per_lookup", "1", "--hidden_size", "32"],
     "din_many": ["--model_type", "din", "--arch_embedding_size", "1000-100-2000-2000",
                  "--user_behavior_tables", "10", "--arch_sparse_feature_size", "32",
                  "--arch_mlp_bot", "8-4", "--arch_mlp_top", "200-80-2",
@@ -107,6 +111,20 @@ def golden_requests(name):
     return GOLDEN_STANDALONE.get(name, GOLDEN_REQUESTS)
 
 
+def apply_golden_params(c, z):
+    """DIEN: the recurrent cells' weights are created by the framework's initialiser when the
+    reference runs model.param_init_net (not from the numpy stream), so the golden file records
+    them; use exactly those for the comparison.  No-op for every other graph."""
+    if c.spec.model_type != "dien":
+        return c
+    from deeprecsys_b200 import _lib
+    for cell in range(2):
+        pre = "%s/params/rnn_%d/" % (c.name, cell)
+        c.fcs[(_lib.MLP_RNN_BASE + cell, 0)] = (z[pre + "i2h_w"], z[pre + "i2h_b"])
+        c.fcs[(_lib.MLP_RNN_BASE + cell, 1)] = (z[pre + "gates_t_w"], z[pre + "gates_t_b"])
+    return c
+
+
 def golden_stages(z, name, batch_id, B, spec):
     """Map the reference's blob names to the stage dict of oracle.numpy_oracle.forward."""
     tag = name + "@standalone" if name in GOLDEN_STANDALONE else name
@@ -146,6 +164,10 @@ def golden_stages(z, name, batch_id, B, spec):
         st["interact"] = g("feat_int")
         st["out"] = g("prob_click")
         return st
+    elif spec.model_type == "dien":
+        st["bot"] = [g("rnn_1/hidden_t_last").reshape(B, -1)]
+        st["interact"] = g("gru:::concat")
+        st["top"] = mlp_tags("top", len(mlps[1]) - 1, "prob_click")
     elif spec.model_type == "din":
         st["bot"] = [g("atten_out")]
         st["interact"] = g("top_fc_in")

@@ -13,8 +13,8 @@ import pytest
 
 from deeprecsys_b200 import _lib
 from deeprecsys_b200.engine import AccelEngine
-from tests.helpers import (GOLDEN_MAX_BATCH, SMALL, golden_requests, golden_stages,
-                           load_ref_golden, make_case, request)
+from tests.helpers import (GOLDEN_MAX_BATCH, SMALL, apply_golden_params, golden_requests,
+                           golden_stages, load_ref_golden, make_case, request)
 
 pytestmark = pytest.mark.gpu
 
@@ -36,6 +36,9 @@ def _check(c, eng, ref, B, atol_out, atol_hidden, rtol):
                                    atol=atol_hidden)
     else:
         np.testing.assert_allclose(inter, ref["interact"], rtol=rtol, atol=atol_hidden)
+    if spec.model_type == "dien":                 # last hidden state of the second recurrent cell
+        np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_BOT), ref["bot"][0], rtol=rtol,
+                                   atol=atol_hidden)
     for tk, head in enumerate(ref.get("tasks", [])):
         for k, want in enumerate(head):
             np.testing.assert_allclose(eng.fetch_stage(_lib.STAGE_TASK, tk * 256 + k), want,
@@ -52,7 +55,7 @@ def _check(c, eng, ref, B, atol_out, atol_hidden, rtol):
                                                             ("tf32x3", 1e-5, 5e-5)])
 @pytest.mark.parametrize("name", sorted(SMALL))
 def test_cuda_path_reproduces_reference_blobs(name, precision, atol_out, atol_hidden):
-    c = make_case(name, num_batches=2, max_batch=GOLDEN_MAX_BATCH, seed=123)
+    c = apply_golden_params(make_case(name, num_batches=2, max_batch=GOLDEN_MAX_BATCH, seed=123), Z)
     with AccelEngine(args=c.args, max_batch=GOLDEN_MAX_BATCH, precision=precision) as eng:
         eng.set_option("tap_hidden", 1)
         eng.load_parameters(c.tables, c.fcs)

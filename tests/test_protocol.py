@@ -115,7 +115,7 @@ def test_engine_never_dies_silently_when_init_fails():
 
 
 def test_engine_unsupported_model_still_terminates():
-    out = _run_engine(FakeBackend, [_req(0, 4)], model_name="dien")
+    out = _run_engine(FakeBackend, [_req(0, 4)], model_name="not_a_model")
     assert [r.out_batch_size for r in out] == [0]
 
 

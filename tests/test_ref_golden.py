@@ -14,8 +14,8 @@ import numpy as np
 import pytest
 
 from oracle import numpy_oracle as O
-from tests.helpers import (GOLDEN_MAX_BATCH, SMALL, golden_requests, golden_stages,
-                           load_ref_golden, make_case, request)
+from tests.helpers import (GOLDEN_MAX_BATCH, SMALL, apply_golden_params, golden_requests,
+                           golden_stages, load_ref_golden, make_case, request)
 
 Z = load_ref_golden()
 
@@ -26,7 +26,7 @@ def _close(a, b):
 
 @pytest.mark.parametrize("name", sorted(SMALL))
 def test_oracle_reproduces_reference_blobs(name):
-    c = make_case(name, num_batches=2, max_batch=GOLDEN_MAX_BATCH, seed=123)
+    c = apply_golden_params(make_case(name, num_batches=2, max_batch=GOLDEN_MAX_BATCH, seed=123), Z)
     for batch_id, B in golden_requests(name):
         dense, ids, lengths = request(c, batch_id, B)
         st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
