@@ -761,22 +761,30 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
         CU(cudaGetLastError());
         e->launches += 1;
         const int64_t seq_rows = (int64_t)N * cap;
-        const int rnn_grid = ceil_div(rows, kRnnRows);
-        const size_t rnn_smem = rnn_smem_bytes(H);
+        // register-tiled recurrence when H % 4 == 0 (16-byte weight reads), generic otherwise
+        const bool fast = (H % 4 == 0);
+        const int rnn_grid = ceil_div(rows, fast ? kRnnRows4 : kRnnRows);
+        const size_t rnn_smem = fast ? rnn4_smem_bytes(H) : rnn_smem_bytes(H);
+        auto recur = [&](const Layer& g, float* all_out, float* last_out, int64_t ld_last) {
+          if (fast)
+            k_rnn_tanh4<<<rnn_grid, kRnnThreads, rnn_smem, ln.stream>>>(ln.rnn_pre, g.W, g.b, N,
+                                                                        rows, H, all_out, last_out,
+                                                                        ld_last);
+          else
+            k_rnn_tanh<<<rnn_grid, kRnnThreads, rnn_smem, ln.stream>>>(ln.rnn_pre, g.W, g.b, N,
+                                                                       rows, H, all_out, last_out,
+                                                                       ld_last);
+          e->launches += 1;
+        };
         // cell 0: i2h over all N steps at once, then the recurrence
         TRY(launch_fc(e, ln, e->rnn[0].layers[0], ln.seq, D, 0, seq_rows, ln.rnn_pre, H, 0,
                       N * rows));
-        k_rnn_tanh<<<rnn_grid, kRnnThreads, rnn_smem, ln.stream>>>(
-            ln.rnn_pre, e->rnn[0].layers[1].W, e->rnn[0].layers[1].b, N, rows, H, ln.rnn_h0,
-            nullptr, 0);
+        recur(e->rnn[0].layers[1], ln.rnn_h0, nullptr, 0);
         // cell 1 reads every hidden state of cell 0; only its last state is used (dien.py:380)
         TRY(launch_fc(e, ln, e->rnn[1].layers[0], ln.rnn_h0, H, 0, seq_rows, ln.rnn_pre, H, 0,
                       N * rows));
-        k_rnn_tanh<<<rnn_grid, kRnnThreads, rnn_smem, ln.stream>>>(
-            ln.rnn_pre, e->rnn[1].layers[1].W, e->rnn[1].layers[1].b, N, rows, H, nullptr, ln.R,
-            e->ld_R);
+        recur(e->rnn[1].layers[1], nullptr, ln.R, e->ld_R);
         CU(cudaGetLastError());
-        e->launches += 2;
         const int cols[3] = {0, T - 2, T - 1};       // profile, candidate ad, context (dien.py:418-420)
         for (int k = 0; k < 3; ++k) {
           k_copy_cols<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(
@@ -1173,6 +1181,8 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
         if (!attr_set) {
           CUB(cudaFuncSetAttribute(k_rnn_tanh, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)rnn_smem_bytes(kRnnMaxH)));
+          CUB(cudaFuncSetAttribute(k_rnn_tanh4, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)rnn4_smem_bytes(kRnnMaxH)));
           attr_set = true;
         }
       }

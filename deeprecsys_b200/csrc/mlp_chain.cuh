@@ -334,20 +334,7 @@ struct ChainLayerHost {
   int64_t ld_tap;
 };
 
-inline bool tc_make_map_bk(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols,
-                           int64_t ld, int box_rows, int bk) {
-  PFN_encodeTiled enc = tc_encode_fn();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
+// tensor maps: tc_make_map_bk (mlp_tc.cuh), cached per (address, shape, pitch, box)
 
 inline bool chain_supported(const ChainLayerHost* layers, int n, int64_t ldx, const float* X) {
   if (n < 1 || n > kChainMaxLayers || tc_encode_fn() == nullptr) return false;

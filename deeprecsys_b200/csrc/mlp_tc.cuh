@@ -24,6 +24,10 @@
 // (warp w owns TMEM lanes 32*(w%4)..+31).  grid = (ceil(N/BN), ceil(M/128), units).
 #pragma once
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include <cuda.h>
 
 #include "common.cuh"
@@ -343,20 +347,49 @@ inline PFN_encodeTiled tc_encode_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major view [rows, cols] with row pitch ld floats; box = [box_rows, 32 floats]
-inline bool tc_make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld,
-                        int box_rows) {
+// 2-D fp32 row-major view [rows, cols] with row pitch ld floats; box = [box_rows, 32 floats].
+// A descriptor depends only on (address, shape, pitch, box), and the serving loop asks for the
+// same few over and over (weights, per-lane activation buffers), so encoded descriptors are
+// cached: cuTensorMapEncodeTiled costs ~1 us and a query needs 7 of them.
+struct TcMapKey {
+  const void* ptr; int64_t rows, cols, ld; int box_rows, bk;
+  bool operator<(const TcMapKey& o) const {
+    return std::tie(ptr, rows, cols, ld, box_rows, bk) <
+           std::tie(o.ptr, o.rows, o.cols, o.ld, o.box_rows, o.bk);
+  }
+};
+
+// bk: floats of K per box (32 -> SWIZZLE_128B, 16 -> SWIZZLE_64B)
+inline bool tc_make_map_bk(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols,
+                           int64_t ld, int box_rows, int bk) {
+  static std::mutex mu;
+  static std::map<TcMapKey, CUtensorMap> cache;
+  const TcMapKey key{ptr, rows, cols, ld, box_rows, bk};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return true; }
+  }
   PFN_encodeTiled enc = tc_encode_fn();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   kTcBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 4096) cache.clear();          // bounded: engines come and go in tests
+  cache[key] = *map;
+  return true;
+}
+
+inline bool tc_make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows) {
+  return tc_make_map_bk(map, ptr, rows, cols, ld, box_rows, kTcBK);
 }
 
 inline int tc_pick_bn(int N) {
