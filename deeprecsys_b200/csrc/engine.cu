@@ -515,6 +515,17 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
   // one segment per lane group and round: with few tables per rank (table-sharded RMC1 on 8
   // GPUs gathers ONE table) a tile must carry up to `groups` samples or lane groups sit idle
   if (SB > 64) SB = 64;
+  // short segments (WnD / NCF / DIEN: one lookup per table): a tile of groups/T samples is a few
+  // dozen rows, and the per-tile work (offsets, barriers, index staging) dominates -> grow the
+  // tile to ~256 rows, within the persistent kernel's register budget for offsets
+  {
+    const int64_t rows_per_sample = (int64_t)(T > 0 ? T : 1) * (avg_len > 0 ? avg_len : 1);
+    int want = (int)((256 + rows_per_sample - 1) / rows_per_sample);
+    if (want > 64) want = 64;
+    while (want > SB && (int64_t)T * (want + 1) > kPersistOffRegs * kSlsThreads) --want;
+    if (want > SB) SB = want;
+  }
+  while (dot && SB > 1 && sls_smem_bytes(T, SB, 0, D, true) > 64 * 1024) --SB;   // pooled tile of the fused dot
   int idx_cap = 0;
   if (avg_len >= 8) {
     int64_t want = ((int64_t)SB * avg_len + 3 + 3) & ~int64_t(3);
