@@ -185,6 +185,11 @@ def accelInferenceEngine(args,
 
     inferenceEngineReadyQueue.put(True)
 
+    # multiprocessing.Queue.put hands the response to a feeder thread; while this loop is busy
+    # (requests always pending) that thread only gets the GIL at a switch interval, 5 ms by
+    # default -> responses would leave up to 5 ms late exactly when the engine is loaded
+    sys.setswitchinterval(1e-4)
+
     # Packets are served in arrival order with up to ``depth`` of them in flight on the GPU;
     # a response is stamped when its own result has landed in host memory.
     import collections
