@@ -185,6 +185,7 @@ struct drs_engine {
 
   // gather launch geometry
   int lpr = 0, SB = 1, idx_cap = 0;
+  bool short_seg = false;
   size_t sls_smem = 0;
   bool table_major = false;
 
@@ -459,31 +460,39 @@ int launch_gather_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid
   return DRS_OK;
 }
 
-template <int LPR>
+template <int LPR, bool SHORT>
 int launch_gather_persist_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid,
                             size_t smem) {
   static bool attr_set = false;
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(k_sls_gather_persist<LPR>,
+    CU(cudaFuncSetAttribute(k_sls_gather_persist<LPR, SHORT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  k_sls_gather_persist<LPR><<<grid, kSlsThreads, smem, st>>>(p);
+  k_sls_gather_persist<LPR, SHORT><<<grid, kSlsThreads, smem, st>>>(p);
   CU(cudaGetLastError());
   e->launches += 1;
   return DRS_OK;
 }
 
+template <bool SHORT>
+int launch_gather_persist_s(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
+                            size_t smem) {
+  switch (lpr) {
+    case 1:  return launch_gather_persist_t<1, SHORT>(e, st, p, grid, smem);
+    case 2:  return launch_gather_persist_t<2, SHORT>(e, st, p, grid, smem);
+    case 4:  return launch_gather_persist_t<4, SHORT>(e, st, p, grid, smem);
+    case 8:  return launch_gather_persist_t<8, SHORT>(e, st, p, grid, smem);
+    case 16: return launch_gather_persist_t<16, SHORT>(e, st, p, grid, smem);
+    default: return launch_gather_persist_t<32, SHORT>(e, st, p, grid, smem);
+  }
+}
+
+// short segments take the multi-segment path
 int launch_gather_persist(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
                           size_t smem) {
-  switch (lpr) {
-    case 1:  return launch_gather_persist_t<1>(e, st, p, grid, smem);
-    case 2:  return launch_gather_persist_t<2>(e, st, p, grid, smem);
-    case 4:  return launch_gather_persist_t<4>(e, st, p, grid, smem);
-    case 8:  return launch_gather_persist_t<8>(e, st, p, grid, smem);
-    case 16: return launch_gather_persist_t<16>(e, st, p, grid, smem);
-    default: return launch_gather_persist_t<32>(e, st, p, grid, smem);
-  }
+  if (p.short_seg) return launch_gather_persist_s<true>(e, st, p, lpr, grid, smem);
+  return launch_gather_persist_s<false>(e, st, p, lpr, grid, smem);
 }
 
 template <bool DOT>
@@ -502,7 +511,8 @@ int launch_gather_lpr(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lp
 
 // table_major: a CTA tile = SB samples of ONE table (see SlsLaunch::tiles_per_table)
 void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_out,
-                 int* idx_cap_out, size_t* smem_out, bool table_major = false) {
+                 int* idx_cap_out, size_t* smem_out, bool table_major = false,
+                 bool* short_out = nullptr) {
   if (table_major) T = 1;
   int lpr = 0;
   if (D % 4 == 0) {
@@ -527,7 +537,10 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
   }
   while (dot && SB > 1 && sls_smem_bytes(T, SB, 0, D, true) > 64 * 1024) --SB;   // pooled tile of the fused dot
   int idx_cap = 0;
-  if (avg_len >= 8) {
+  // short segments: only the persistent kernel's SHORT path stages their (tiny) index spans
+  const bool short_seg = avg_len < 8;
+  if (short_out) *short_out = short_seg;
+  if (avg_len >= 8 || (short_out && avg_len >= 1)) {
     int64_t want = ((int64_t)SB * avg_len + 3 + 3) & ~int64_t(3);
     if (sls_smem_bytes(T, SB, (int)want, D, dot) <= 96 * 1024) idx_cap = (int)want;
   }
@@ -571,7 +584,8 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
   // persistent path: vectorised rows, no dot fusion, offsets fit the per-thread registers
   if (e->gather_ctas_per_sm > 0 && !dot && !e->table_major && e->lpr > 0 &&
       p.T * (e->SB + 1) <= kPersistOffRegs * kSlsThreads) {
-    const size_t smem = sls_persist_smem_bytes(p.T, e->SB, e->idx_cap);
+    p.short_seg = e->short_seg ? 1 : 0;
+    const size_t smem = sls_persist_smem_bytes(p.T, e->SB, e->idx_cap, e->short_seg);
     if (smem <= 100 * 1024) {
       const int cap = e->n_sm * e->gather_ctas_per_sm;
       return launch_gather_persist(e, ln.stream, p, e->lpr, grid < cap ? grid : cap, smem);
@@ -1291,7 +1305,7 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
     e->table_major = !dlrm_dot && ord && std::strcmp(ord, "table") == 0;
   }
   plan_gather(T, D, avg_len, dlrm_dot, &e->lpr, &e->SB, &e->idx_cap, &e->sls_smem,
-              e->table_major);
+              e->table_major, &e->short_seg);
 
   TRYB(rewrite_all_descs(e));
   TRYB(sync_all(e));
@@ -1911,7 +1925,7 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
         e->spec.max_lookups_per_table > 0 ? e->spec.max_lookups_per_table : e->spec.max_batch;
     const int64_t avg_len = ceil_div64(max_lk, (int64_t)e->spec.max_batch * world);
     plan_gather((int)e->owned.size() > 0 ? (int)e->owned.size() : 1, e->D, avg_len, false, &e->lpr,
-                &e->SB, &e->idx_cap, &e->sls_smem, e->table_major);
+                &e->SB, &e->idx_cap, &e->sls_smem, e->table_major, &e->short_seg);
   }
   return rewrite_all_descs(e);
 }

@@ -72,6 +72,9 @@ struct SlsLaunch {
   // resident segments walk the table in ascending order roughly in lockstep and concurrent row
   // reads fall into a narrow band of the table (DRAM page locality, L2 hits on shared rows).
   int tiles_per_table;
+  // short segments (avg length < 8: WnD / NCF / DIEN / DIN): the persistent kernel's SHORT
+  // instantiation walks kSlsShort segments per lane group at once
+  int short_seg;
 };
 
 __host__ __device__ inline size_t sls_smem_bytes(int T, int SB, int idx_cap, int D, bool fuse_dot) {
@@ -131,6 +134,49 @@ __device__ __forceinline__ float4 sls_segment_vec4(const float* __restrict__ row
       }
   }
   return acc;
+}
+
+
+// Short segments (WnD / NCF / DIEN / DIN have 1-3 lookups per table): one lane group walks
+// kSlsShort segments AT ONCE — row j of each
+// of them is loaded before any add — so that kSlsShort independent row reads are in flight per
+// group instead of one.  Inside every segment the adds still happen in index order.
+constexpr int kSlsShort = 4;
+
+struct ShortSeg {
+  const float* rows_lane;   // table base + this lane's column offset
+  const int32_t* ids;       // table's id array: TMA-staged shared copy (rebased) or global
+  uint32_t n_rows;
+  int beg, end;
+};
+
+__device__ __forceinline__ void sls_short_segments(const ShortSeg (&sg)[kSlsShort], int D,
+                                                   float4 (&acc)[kSlsShort], int* err_flag) {
+  int maxlen = 0;
+#pragma unroll
+  for (int u = 0; u < kSlsShort; ++u) {
+    acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    maxlen = max(maxlen, sg[u].end - sg[u].beg);
+  }
+  for (int j = 0; j < maxlen; ++j) {
+    float4 v[kSlsShort];
+    bool live[kSlsShort];
+#pragma unroll
+    for (int u = 0; u < kSlsShort; ++u) {
+      live[u] = sg[u].beg + j < sg[u].end;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[u]) {
+        const int32_t id = sg[u].ids[sg[u].beg + j];     // shared (TMA-staged) or global
+        if ((uint32_t)id < sg[u].n_rows) v[u] = ldg_stream_f4(sg[u].rows_lane + (int64_t)id * D);
+        else *err_flag = 1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSlsShort; ++u)
+      if (live[u]) {
+        acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+      }
+  }
 }
 
 // LPR: lanes per row (D == 4*LPR).  LPR == 0 selects the generic any-D path
@@ -302,14 +348,20 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
 // neighbouring lane to run *concurrently* with the gather (engine.cu lanes).
 constexpr int kPersistOffRegs = 2;     // offsets per thread kept in registers: T*(SB+1) <= 512
 
-__host__ __device__ inline size_t sls_persist_smem_bytes(int T, int SB, int idx_cap) {
+__host__ __device__ inline size_t sls_persist_smem_bytes(int T, int SB, int idx_cap,
+                                                         bool short_seg = false) {
   size_t b = 32;                                              // two mbarriers (+pad)
   b += 2 * (size_t)T * idx_cap * sizeof(int32_t);             // index spans, double-buffered
   b += 2 * (size_t)T * (SB + 1) * sizeof(int32_t);            // offsets, double-buffered
+  b = (b + 15) & ~size_t(15);
+  if (short_seg) b += (size_t)T * sizeof(SlsTableDesc);       // table descriptors (SHORT path)
   return (b + 15) & ~size_t(15);
 }
 
-template <int LPR>
+// SHORT: compile the multi-segment path for short segments (ids from global memory) instead of
+// the long-segment path — a separate instantiation so that its extra registers do not lower the
+// occupancy of the HBM-bound long-segment kernel.
+template <int LPR, bool SHORT>
 __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);            // bar[0], bar[1]
@@ -369,6 +421,17 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
 
   int tile = blockIdx.x;
   if (tile >= ntiles) return;
+  // SHORT: a segment is a handful of rows, so even the 40-byte descriptor fetch from global
+  // memory would sit on its critical path -> keep the descriptors in shared memory
+  const SlsTableDesc* sdesc = tabs;
+  if (SHORT) {
+    size_t o = 32 + (2 * idx_words + 2 * (size_t)noff) * sizeof(int32_t);
+    o = (o + 15) & ~size_t(15);
+    SlsTableDesc* sd = reinterpret_cast<SlsTableDesc*>(smem_raw + o);
+    for (int i = tid; i < T * (int)(sizeof(SlsTableDesc) / 8); i += kSlsThreads)
+      reinterpret_cast<uint64_t*>(sd)[i] = reinterpret_cast<const uint64_t*>(tabs)[i];
+    sdesc = sd;                        // visible after the first __syncthreads below
+  }
   int32_t regs[kPersistOffRegs];
   load_offs(tile, regs);
   if (use_smem_idx && tid == 0) {
@@ -398,6 +461,46 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
     const int32_t* so = soff0 + (size_t)cur * noff;
     const int32_t* si = sidx0 + (size_t)cur * idx_words;
     const int nseg = sbe * T;
+    if (SHORT) {                         // short segments: kSlsShort of them per group at once
+      for (int s0 = group; s0 < nseg; s0 += ngroups * kSlsShort) {
+        ShortSeg sg[kSlsShort];
+        float* dst[kSlsShort];
+#pragma unroll
+        for (int u = 0; u < kSlsShort; ++u) {
+          const int s = s0 + u * ngroups;
+          dst[u] = nullptr;
+          sg[u].beg = sg[u].end = 0;
+          sg[u].rows_lane = nullptr; sg[u].ids = nullptr; sg[u].n_rows = 0;
+          if (s < nseg) {
+            const int t = s / sbe, lb = s - t * sbe;
+            const SlsTableDesc& td = sdesc[t];
+            const int tile_beg = so[t * SB1], tile_end = so[t * SB1 + sbe];
+            const int a0 = tile_beg & ~3;
+            const bool in_smem = use_smem_idx && (((tile_end - a0 + 3) & ~3) <= p.idx_cap);
+            sg[u].rows_lane = td.rows + lane * 4;
+            sg[u].ids = in_smem ? si + (size_t)t * p.idx_cap - a0 : td.idx;
+            sg[u].n_rows = (uint32_t)td.n_rows;
+            sg[u].beg = so[t * SB1 + lb];
+            sg[u].end = so[t * SB1 + lb + 1];
+            const int64_t b = b0 + lb;
+            dst[u] = (p.shard_S > 0 ? p.peer_out[b / p.shard_S] + (b % p.shard_S) * p.ld_out
+                                    : p.out + b * p.ld_out) + td.dst_col + lane * 4;
+          }
+        }
+        float4 acc[kSlsShort];
+        sls_short_segments(sg, p.D, acc, p.err_flag);
+#pragma unroll
+        for (int u = 0; u < kSlsShort; ++u) {
+          if (!dst[u]) continue;
+          if (p.vec_store) {
+            *reinterpret_cast<float4*>(dst[u]) = acc[u];
+          } else {
+            dst[u][0] = acc[u].x; dst[u][1] = acc[u].y; dst[u][2] = acc[u].z; dst[u][3] = acc[u].w;
+          }
+        }
+      }
+      continue;
+    }
     for (int s = group; s < nseg; s += ngroups) {
       const int t = s / sbe, lb = s - t * sbe;
       const SlsTableDesc td = tabs[t];
