@@ -156,19 +156,75 @@ class AccelBackend(object):
 BACKEND_FACTORY = AccelBackend
 
 
+def _die_with_parent():
+    """Linux: deliver SIGTERM to this process when its parent dies (DeepRecSys.py:179 ends the
+    run by terminate()-ing the engine processes; sibling GPU workers must not outlive that)."""
+    try:
+        import ctypes
+        import signal
+        ctypes.CDLL("libc.so.6", use_errno=True).prctl(1, signal.SIGTERM)     # PR_SET_PDEATHSIG
+    except Exception:
+        pass
+
+
+def _spawn_siblings(args, requestQueue, engine_id, responseQueue):
+    """--accel_gpus N > 1: the single accel slot of DeepRecSys.py fronts N GPUs.  N-1 sibling
+    processes (one per extra GPU, replicas of the whole model) consume the SAME accelRequestQueue
+    and answer on the SAME responseQueue.  Forked before this process touches CUDA."""
+    n = int(getattr(args, "accel_gpus", 1) or 1)
+    if n <= 1:
+        return [], None
+    if getattr(args, "accel_shard", "replica") != "replica":
+        raise ValueError("--accel_shard %s: the Queue-fed engine serves replicas only (sharded "
+                         "ranks must see every query in lock-step; see bench.py --shard)"
+                         % args.accel_shard)
+    import copy
+    import multiprocessing as mp
+    cur = mp.current_process()
+    was_daemon = cur._config.get("daemon")
+    cur._config["daemon"] = False      # DeepRecSys.py:71 marks engines daemonic; daemons may not fork
+    try:
+        ctx = mp.get_context("fork")
+        ready = ctx.Queue()
+        procs = []
+        for g in range(1, n):
+            a = copy.copy(args)
+            a.accel_device = int(getattr(args, "accel_device", 0)) + g
+            a.accel_gpus = 1
+            p = ctx.Process(target=_sibling_main,
+                            args=(a, requestQueue, engine_id, responseQueue, ready))
+            p.start()
+            procs.append(p)
+    finally:
+        cur._config["daemon"] = was_daemon
+    return procs, ready
+
+
+def _sibling_main(args, requestQueue, engine_id, responseQueue, readyQueue):
+    _die_with_parent()
+    _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, sibling=True)
+
+
 def accelInferenceEngine(args,
                          requestQueue=None,
                          engine_id=None,
                          responseQueue=None,
                          inferenceEngineReadyQueue=None):
-    np.random.seed(args.numpy_rand_seed)
-    np.set_printoptions(precision=args.print_precision)
-
     if requestQueue is None:
         print("If you want to run Accel in isolation please use bench.py / "
               "deeprecsys_b200.serve directly")
         sys.stdout.flush()
         sys.exit()
+    _engine_process(args, requestQueue, engine_id, responseQueue, inferenceEngineReadyQueue,
+                    sibling=False)
+
+
+def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):
+    np.random.seed(args.numpy_rand_seed)
+    np.set_printoptions(precision=args.print_precision)
+
+    siblings, sibling_ready = ([], None) if sibling else _spawn_siblings(
+        args, requestQueue, engine_id, responseQueue)
 
     backend, failure = None, None
     if args.model_name not in SUPPORTED_MODEL_NAMES:
@@ -183,7 +239,9 @@ def accelInferenceEngine(args,
         print("[Accel] " + failure)
         sys.stdout.flush()
 
-    inferenceEngineReadyQueue.put(True)
+    for _ in siblings:                     # one ready token for the whole accel slot
+        sibling_ready.get()
+    readyQueue.put(True)
 
     # multiprocessing.Queue.put hands the response to a feeder thread; while this loop is busy
     # (requests always pending) that thread only gets the GIL at a switch interval, 5 ms by
@@ -228,6 +286,7 @@ def accelInferenceEngine(args,
         debugPrint(args, "Accel", "Sending response back")
         responseQueue.put(response)
 
+    multi = sibling or bool(siblings)
     while True:
         if inflight and (len(inflight) >= depth or requestQueue.empty()):
             finish_oldest()
@@ -237,12 +296,20 @@ def accelInferenceEngine(args,
         debugPrint(args, "Accel", "Pulled request")
 
         if request is None:
+            # With several processes on one queue the sentinel keeps circulating: whoever takes it
+            # puts it back for the others (requests precede it in the FIFO, so the queue has room)
+            if multi:
+                requestQueue.put(None)
             while inflight:
                 finish_oldest()
-            debugPrint(args, "Accel", "Sending final done signal")
-            responseQueue.put(None)
             if backend is not None:
                 backend.close()
+            if sibling:
+                return                     # responses are flushed when the process exits
+            for p in siblings:             # their responses must precede the final sentinel
+                p.join(timeout=120)
+            debugPrint(args, "Accel", "Sending final done signal")
+            responseQueue.put(None)
             return
 
         start_time = time.time()

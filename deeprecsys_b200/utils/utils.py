@@ -116,8 +116,12 @@ REFERENCE_FLAGS = (
 ACCEL_FLAGS = (
     ("accel_device", int, 0),            # CUDA ordinal used by the accel engine
     ("accel_precision", str, "fp32"),    # fp32 (parity) | tf32x3 | tf32 (tensor-core MLP)
-    ("accel_shard", str, "replica"),     # replica | table   (multi-GPU, one process per GPU)
+    ("accel_shard", str, "replica"),     # replica: --accel_gpus replicas behind the accel slot.
+                                         # table/row sharding needs lock-step ranks and is driven
+                                         # by bench.py / torchrun, not by the Queue-fed engine
     ("accel_upload_inputs", _T, False),  # H2D per query instead of pre-staged batches
+    ("accel_gpus", int, 1),              # GPUs behind the single accel slot (replicas; sibling
+                                         # processes share accelRequestQueue / responseQueue)
 )
 
 

@@ -57,9 +57,9 @@ class BrokenBackend(object):
         raise SystemExit("init exploded")
 
 
-def _run_engine(factory, requests, model_name="rm1"):
+def _run_engine(factory, requests, model_name="rm1", extra=()):
     args = cli(SMALL_SYSTEM[:-6] + ["--model_name", model_name, "--num_batches", "6",
-                                    "--max_mini_batch_size", "64"])
+                                    "--max_mini_batch_size", "64"] + list(extra))
     ctx = mp.get_context("fork")
     rq, resp, ready = ctx.Queue(), ctx.Queue(), ctx.Queue()
     old = accel_mod.BACKEND_FACTORY
@@ -117,6 +117,35 @@ def test_engine_never_dies_silently_when_init_fails():
 def test_engine_unsupported_model_still_terminates():
     out = _run_engine(FakeBackend, [_req(0, 4)], model_name="not_a_model")
     assert [r.out_batch_size for r in out] == [0]
+
+
+class PidBackend(FakeBackend):
+    """Reports which process served a request through out_batch_size-independent side channel."""
+    def __init__(self, args):
+        FakeBackend.__init__(self, args)
+        self.dir = os.environ["DRS_TEST_PID_DIR"]
+        self.device = int(args.accel_device)
+
+    def serve(self, batch_id, batch_size):
+        open(os.path.join(self.dir, "%d_%d" % (os.getpid(), self.device)), "a").close()
+        time.sleep(0.002)                      # let the other processes get their share
+        return FakeBackend.serve(self, batch_id, batch_size)
+
+
+def test_accel_gpus_siblings_share_the_accel_slot(tmp_path, monkeypatch):
+    """--accel_gpus 3: the engine (a daemonic process, as DeepRecSys.py:71 makes it) forks two
+    sibling processes that consume the same accelRequestQueue; every request is answered exactly
+    once, the parent sees ONE ready token and ONE final sentinel after all responses."""
+    monkeypatch.setenv("DRS_TEST_PID_DIR", str(tmp_path))
+    reqs = [_req(i % 3, 4 + i % 5, epoch=i // 3) for i in range(60)]
+    out = _run_engine(PidBackend, reqs, extra=["--accel_gpus", "3", "--accel_device", "0"])
+    assert len(out) == 60
+    assert sorted((r.epoch, r.batch_id, r.batch_size) for r in out) == \
+        sorted((q.epoch, q.batch_id, q.batch_size) for q in reqs)
+    assert all(r.out_batch_size == r.batch_size for r in out)
+    served = os.listdir(str(tmp_path))
+    assert len({f.split("_")[0] for f in served}) == 3, served          # three processes worked
+    assert sorted(int(f.split("_")[1]) for f in served) == [0, 1, 2]    # on devices 0, 1, 2
 
 
 def test_engine_without_queue_exits_like_the_reference():
