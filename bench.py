@@ -424,6 +424,24 @@ def run_b200(opts):
                "ms_per_step": 1e3 * dt / opts.steps, "ids_dtype": "int32",
                "note": "per step H2D -> kernels -> D2H, steps pipelined over the engine lanes, "
                        "wall clock incl. final sync, max over ranks"}
+        # the same step with int64 ids, the dtype the reference's run_queues receives from
+        # np.array(list) (the Cast to int32 then runs on the GPU): twice the id bytes over PCIe
+        h_idx64, _k5 = pinned_empty((T, B * L), np.int64)
+        h_idx64[:] = lS_i[0]
+        idx64_ptrs = (C.c_void_p * T)(*[h_idx64[t].ctypes.data for t in range(T)])
+        n64 = max(5, opts.steps // 3)
+        for _ in range(3):
+            eng.enqueue_host(den_ptr, idx64_ptrs, 1, len_ptrs, B, out_ptr)
+        eng.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n64):
+            eng.enqueue_host(den_ptr, idx64_ptrs, 1, len_ptrs, B, out_ptr)
+        eng.sync()
+        dt64 = max_over_ranks(time.perf_counter() - t0)
+        e2e["int64_ids"] = {"value": world * B * n64 / dt64, "unit": UNIT, "steps": n64,
+                            "h2d_bytes_per_step": B * (T * L * 8 + T * 4 + spec.m_den * 4)}
+        del h_idx64, _k5
         # per-query latency at the reference's largest query size (1024), same path.
         # NOTE: the first 1024 samples of the staged host batch (inferenceEngine.py:200-215)
         q = min(1024, B)
