@@ -557,7 +557,10 @@ def run_b200(opts):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": opts.steps, "warmup": max(3, opts.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if opts.precision == "fp32" else opts.precision,
+            # the arithmetic the path computes in: the gather/interaction are fp32; the MLP is
+            # fp32 FFMA, or tcgen05 TF32 tensor-core products — "tf32x3" = 3-pass error-compensated
+            # (results within 1e-5 of fp32), "tf32" = single pass
+            "dtype": "f32" if opts.precision == "fp32" else "f32+" + opts.precision,
             "data": "synthetic",
             "config": {"workload": "dlrm_%s (%s) %d tables x %s rows x D=%d, L=%d, "
                                    "%d samples/step (=%d coalesced 1024-item queries), "
