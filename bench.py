@@ -362,9 +362,10 @@ def run_b200(opts):
     for i in range(8):
         eng.enqueue_staged(i % nb, GB)
         eng.sync()
-    n_solo, _, solo_ms, _ = eng.profile_end()
+    n_solo, solo_pre, solo_ms, solo_post = eng.profile_end()
     solo_ms_avg = solo_ms / max(1, n_solo)
     tot = max(1e-9, pre_ms + gather_ms + post_ms)
+    solo_tot = max(1e-9, solo_pre + solo_ms + solo_post)
     roofline = {
         "kernel": "k_sls_gather_persist (multi-table SparseLengthsSum + cat layout)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -382,11 +383,17 @@ def run_b200(opts):
                          if solo_ms_avg > 0 else None,
                          "note": "same launch with one query in flight (no overlap with the MLP "
                                  "kernels of other lanes), CUDA events around the launch"},
-        "step_share": {"pre_gather_mlp": pre_ms / tot, "gather": gather_ms / tot,
-                       "post_gather_mlp": post_ms / tot,
-                       "note": "event-bracketed segments per lane; lanes overlap, so segments of "
-                               "different lanes run concurrently (serialised shares: profiles/ "
-                               "launch list)"},
+        # shares of one step with ONE query in flight (kernels run back to back, like ncu's
+        # serialised launch list in profiles/): comparable with the launch list's shares
+        "step_share": {"pre_gather_mlp": solo_pre / solo_tot, "gather": solo_ms / solo_tot,
+                       "post_gather_mlp": solo_post / solo_tot,
+                       "note": "CUDA-event segments of the step with one query in flight "
+                               "(serialised, comparable with profiles/*launches*.csv)"},
+        "step_share_overlapped": {"pre_gather_mlp": pre_ms / tot, "gather": gather_ms / tot,
+                                  "post_gather_mlp": post_ms / tot,
+                                  "note": "same segments in the timed region: lanes overlap, so "
+                                          "segments of different lanes run concurrently and "
+                                          "each is stretched by the sharing"},
     }
 
     # ---------------- e2e: C-ABI with pinned HOST buffers, H2D + D2H inside
