@@ -174,13 +174,13 @@ def load_traffic(opts, spec, B, sharded):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the gather kernel from the
     committed ``ncu --set full`` capture of this same command (profiles/), or None when the
     capture does not cover this workload."""
-    path = os.path.join(ROOT, "profiles", "r01b_gather_persist_ncu_full_summary.json")
+    path = os.path.join(ROOT, "profiles", "r01f_gather_persist_ncu_full_summary.json")
     if sharded or opts.config != "rm1" or B != 16384 or not os.path.exists(path):
         return None, None
     with open(path) as f:
         cap = json.load(f)
     vals = [l["traffic_bytes_per_launch"] for l in cap["launches"]]
-    return float(np.mean(vals)), "profiles/r01b_gather_persist_ncu_full_summary.json"
+    return float(np.mean(vals)), "profiles/r01f_gather_persist_ncu_full_summary.json"
 
 
 def load_peaks():
