@@ -287,12 +287,23 @@ def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, si
         responseQueue.put(response)
 
     multi = sibling or bool(siblings)
+    import queue as _queue
     while True:
-        if inflight and (len(inflight) >= depth or requestQueue.empty()):
+        if len(inflight) >= depth:
             finish_oldest()
             continue
         debugPrint(args, "Accel", "Trying to pull request")
-        request = requestQueue.get()
+        if inflight:
+            # never block on the queue while a packet is in flight: with sibling processes on
+            # the same queue a request seen by empty() may be taken by somebody else, and the
+            # in-flight packet's response would wait for the next arrival
+            try:
+                request = requestQueue.get(block=False)
+            except _queue.Empty:
+                finish_oldest()
+                continue
+        else:
+            request = requestQueue.get()
         debugPrint(args, "Accel", "Pulled request")
 
         if request is None:

@@ -148,6 +148,45 @@ def test_accel_gpus_siblings_share_the_accel_slot(tmp_path, monkeypatch):
     assert sorted(int(f.split("_")[1]) for f in served) == [0, 1, 2]    # on devices 0, 1, 2
 
 
+class PipelinedBackend(FakeBackend):
+    """submit/complete backend with 3 packets in flight, like the real engine's lanes."""
+    depth = 3
+
+    def submit(self, batch_id, batch_size):
+        return (batch_id, batch_size)
+
+    def complete(self, handle):
+        return FakeBackend.serve(self, *handle)
+
+
+def test_pipelined_siblings_never_sit_on_an_in_flight_packet():
+    """Regression: with several processes on one queue, a process holding an in-flight packet
+    must not block in requestQueue.get() (a request it saw may be taken by a sibling): every
+    response has to come back promptly even when requests trickle in one at a time."""
+    args = cli(SMALL_SYSTEM[:-6] + ["--model_name", "rm1", "--num_batches", "6",
+                                    "--max_mini_batch_size", "64", "--accel_gpus", "3"])
+    ctx = mp.get_context("fork")
+    rq, resp, ready = ctx.Queue(), ctx.Queue(), ctx.Queue()
+    old = accel_mod.BACKEND_FACTORY
+    accel_mod.BACKEND_FACTORY = PipelinedBackend
+    try:
+        p = ctx.Process(target=accel_mod.accelInferenceEngine, args=(args, rq, 7, resp, ready))
+        p.daemon = True
+        p.start()
+    finally:
+        accel_mod.BACKEND_FACTORY = old
+    assert ready.get(timeout=60) is True
+    for burst in range(400):                      # bursts of 2 with idle gaps in between
+        rq.put(_req(burst % 3, 8, epoch=burst))
+        rq.put(_req((burst + 1) % 3, 9, epoch=burst))
+        got = [resp.get(timeout=5), resp.get(timeout=5)]     # both answered without a new arrival
+        assert sorted(r.batch_size for r in got) == [8, 9]
+    rq.put(None)
+    assert resp.get(timeout=60) is None
+    p.join(timeout=30)
+    assert not p.is_alive()
+
+
 def test_engine_without_queue_exits_like_the_reference():
     args = cli(SMALL_SYSTEM)
     with pytest.raises(SystemExit):
