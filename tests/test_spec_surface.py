@@ -158,3 +158,32 @@ def test_slice_request_first_rows_only():
     d, l, i = slice_request(lX, lS_l, lS_i, 1, 4, 3)
     assert d.shape == (4, 5) and l.shape == (2, 4) and i.shape == (2, 12)
     assert np.array_equal(i, lS_i[1][:, :12]) and np.array_equal(d, lX[1][:4])
+
+
+from tests.helpers import CONFIG_DIR  # noqa: E402
+
+
+def test_mtwnd_and_dien_dims_follow_the_reference_builders():
+    """multi_task_wnd.py:340-362,396 and dien.py:386-433."""
+    from deeprecsys_b200.spec import ModelSpec
+    a = cli(["--config_file", os.path.join(CONFIG_DIR, "mtwnd.json")])
+    s = ModelSpec(a)
+    assert s.T == 43 and s.ln_top == [43 * 32 + 512, 1024, 512] and s.ln_task == [512, 256, 128]
+    assert s.n_tasks == a.num_multi_tasks == 1
+    assert s.task_sigmoid_layer == 2          # sigmoid_top = len(ln_top) - 1, applied to the heads
+    assert s.out_dim == s.n_tasks * 128
+    a = cli(["--model_type", "mtwnd", "--arch_embedding_size", "9-9", "--arch_sparse_feature_size", "4",
+             "--arch_mlp_bot", "3", "--arch_mlp_top", "8-8-8", "--arch_mlp_tasks", "8-2-1",
+             "--arch_interaction_op", "cat", "--num_multi_tasks", "2"])
+    s = ModelSpec(a)
+    assert s.task_sigmoid_layer == 0          # layer 3 of a 2-layer head: never reached, all ReLU
+    with pytest.raises(ValueError):            # multi_task_wnd.py:362
+        ModelSpec(cli(["--model_type", "mtwnd", "--arch_embedding_size", "9-9",
+                       "--arch_sparse_feature_size", "4", "--arch_mlp_bot", "3",
+                       "--arch_mlp_top", "8-4", "--arch_mlp_tasks", "8-1",
+                       "--arch_interaction_op", "cat"]))
+    a = cli(["--config_file", os.path.join(CONFIG_DIR, "dien.json")])
+    s = ModelSpec(a)
+    assert s.T == 43 and s.n_steps == 40 and s.hidden_size == 64
+    assert s.ln_top == [64 + 3 * 32, 200, 80, 2] and s.out_dim == 2 and s.m_den == 0
+    assert s.rnn == [(32, 64), (64, 64)]
