@@ -37,8 +37,8 @@ def _digest():
     h.update(" ".join(NVCC_FLAGS).encode())
     for path in _sources():
         with open(path, "rb") as f:
-            h.update(path.encode())
-            h.update(f.read())
+            h.update(os.path.basename(path).encode())   # location-independent: the tree is copied
+            h.update(f.read())                          # to a scratch path on the GPU box
     return h.hexdigest()
 
 
