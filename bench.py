@@ -72,7 +72,20 @@ def parse_args():
                    help="mean inter-arrival times (ms) of the serving run")
     p.add_argument("--system_queries", type=int, default=2000)
     p.add_argument("--seed", type=int, default=123)
+    p.add_argument("--locality", type=str, default=None,
+                   help="ids with temporal reuse instead of uniform-random ones: a stack-distance "
+                        "profile name under deeprecsys_b200/data_generator/profile/ (zipf1.05, "
+                        "zipf1.2) or a path (--data_generation synthetic; not the headline "
+                        "workload — L2 hits raise the gather above the HBM roofline)")
     return p.parse_args()
+
+
+def locality_profile(opts):
+    if not opts.locality:
+        return None
+    shipped = os.path.join(ROOT, "deeprecsys_b200", "data_generator", "profile",
+                           "sd_cumm_" + opts.locality)
+    return shipped if os.path.exists(shipped) else opts.locality
 
 
 def model_args(opts, batch, num_batches):
@@ -80,6 +93,9 @@ def model_args(opts, batch, num_batches):
     cfg = os.path.join(ROOT, "deeprecsys_b200", "models", "configs", CONFIGS[opts.config])
     argv = ["--config_file", cfg, "--num_batches", str(num_batches),
             "--max_mini_batch_size", str(batch), "--numpy_rand_seed", str(opts.seed)]
+    if locality_profile(opts):
+        argv += ["--data_generation", "synthetic", "--data_trace_file", locality_profile(opts),
+                 "--num_indices_per_lookup_fixed", "True"]
     a = cli(argv)
     if opts.interaction:
         a.arch_interaction_op = opts.interaction
@@ -577,8 +593,10 @@ def run_b200(opts):
                        "global_batch": B * world,
                        "parallelism": ("%s-sharded x%d (K1 peer stores over NVLink)"
                                        % (opts.shard, world) if sharded else "replica x%d" % world),
-                       "l2_policy": "inputs larger than L2 (4.1 GB tables, uniform ids; "
-                                    "%d staged batches cycled)" % nb,
+                       "l2_policy": "inputs larger than L2 (4.1 GB tables, %s; "
+                                    "%d staged batches cycled)"
+                                    % ("LRU stack-distance ids, profile %s" % opts.locality
+                                       if opts.locality else "uniform ids", nb),
                        "mlp_precision": opts.precision, "lanes": opts.lanes,
                        "numa_node": numa_node},
             "clocks": clocks, "gpu_launches": int(launches),

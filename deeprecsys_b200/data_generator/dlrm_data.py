@@ -62,14 +62,20 @@ class DLRMDataGenerator(object):
     def __init__(self, args):
         self.args = args
 
-    # reference :33-60 (only the "random" branch is live code there)
+    # reference :33-60 (only the "random" branch is live code there; its "synthetic" branch calls
+    # functions that are not in scope and cannot run — see generate_synthetic_input_data below)
     def generate_input_data(self):
         a = self.args
+        ln_bot = _parse_dash_list(a.arch_mlp_bot)
+        ln_emb = _parse_dash_list(a.arch_embedding_size)
+        if a.data_generation == "synthetic":
+            return self.generate_synthetic_input_data(
+                a.num_batches, a.max_mini_batch_size, a.round_targets,
+                a.num_indices_per_lookup, a.num_indices_per_lookup_fixed,
+                int(ln_bot[0]), ln_emb, a.data_trace_file, a.data_trace_enable_padding)
         if a.data_generation != "random":
             raise SystemExit("ERROR: --data-generation=%s is not supported"
                              % a.data_generation)
-        ln_bot = _parse_dash_list(a.arch_mlp_bot)
-        ln_emb = _parse_dash_list(a.arch_embedding_size)
         return self.generate_random_input_data(
             a.num_batches, a.max_mini_batch_size, a.round_targets,
             a.num_indices_per_lookup, a.num_indices_per_lookup_fixed,
@@ -90,6 +96,65 @@ class DLRMDataGenerator(object):
             ids = np.empty((T, n * L), dtype=np.int32)
             for t, rows in enumerate(ln_emb):
                 ids[t] = _draw_distinct_groups(int(rows), n, L).reshape(-1)
+            lS_i.append(ids)
+            lS_l.append(np.full((T, n), L, dtype=np.int32))
+        return num_batches, lX, lS_l, lS_i
+
+    def generate_synthetic_input_data(self, num_batches, mini_batch_size, round_targets,
+                                      num_indices_per_lookup, num_indices_per_lookup_fixed,
+                                      m_den, ln_emb, trace_file, enable_padding=False):
+        """``--data_generation synthetic``: ids with temporal locality.
+
+        The reference's branch (dlrm_data_caffe2.py:48-56,152-227) is dead code — it calls
+        module-level names that only exist as class attributes — so there is no behaviour to
+        reproduce; what is built here is the flow its tools describe (data_generator/README.md:
+        trace_profile.py -> profile/sd_cumm -> trace_generator.py -> one long trace per table of
+        num_batches * mini_batch_size * pooling_factor ids), wired into the generator:
+
+          * table t reads its stack-distance profile from ``trace_file`` with every "j" replaced
+            by t (the reference's convention, :196), or from ``trace_file`` itself when that
+            per-table file does not exist (one profile shared by all tables, e.g. the shipped
+            profile/sd_cumm);
+          * a two-line profile (trace_profile.py's output) takes the order of first references
+            from one ``np.random.permutation(rows)`` per table, drawn in table order before the
+            first batch — the seeded numpy stream, where the reference's script uses python's
+            unseeded ``random.sample`` — a three-line profile (dlrm_data_caffe2.py:380-393)
+            carries that order itself;
+          * per batch: dense ``rand(n, m_den)`` as in the random mode, then for each table the
+            next n*L ids of that table's LRU-stack trace (one uniform draw per id); reuse
+            carries across samples and batches;
+          * lookups keep the fixed length L the engines' request slicing needs
+            (inferenceEngine.py:204-206), in trace order; an id may repeat inside a lookup
+            (SparseLengthsSum then adds that row twice).
+        """
+        import os
+        from deeprecsys_b200.data_generator.trace_generator import (LruTraceGenerator,
+                                                                    read_dist_from_file)
+        if not num_indices_per_lookup_fixed:
+            raise SystemExit("ERROR: --data_generation=synthetic needs "
+                             "--num_indices_per_lookup_fixed (requests are sliced as B*L ids)")
+        n, L, T = int(mini_batch_size), int(num_indices_per_lookup), len(ln_emb)
+        traces = []
+        for t, rows in enumerate(ln_emb):
+            path = str(trace_file).replace("j", str(t))
+            if not os.path.exists(path):
+                path = str(trace_file)
+            dist = read_dist_from_file(path)
+            if len(dist) == 3:
+                order = np.asarray(dist[0], dtype=np.int64)
+                if order.size and (order.min() < 0 or order.max() >= int(rows)):
+                    print("WARNING: distribution is inconsistent with embedding "
+                          "table size (using mod to recover and continue)")      # ref :207-215
+                    order = np.mod(order, int(rows))
+            else:
+                order = np.random.permutation(int(rows))
+            traces.append(LruTraceGenerator(order, dist[-2], dist[-1], enable_padding))
+        lX, lS_l, lS_i = [], [], []
+        for _ in range(num_batches):
+            lX.append(np.random.rand(n, m_den).astype(np.float32))
+            ids = np.empty((T, n * L), dtype=np.int32)
+            for t in range(T):
+                ids[t] = traces[t].generate(n * L)
             lS_i.append(ids)
             lS_l.append(np.full((T, n), L, dtype=np.int32))
         return num_batches, lX, lS_l, lS_i

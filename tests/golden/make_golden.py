@@ -12,6 +12,9 @@ Writes (small, committed):
                         seeded cases, plus the next 4 doubles of the RNG stream
   rm1_probe.json        first values of the full-size dlrm_rm1.json dataset, seed 123
   packets.json          attribute names of the reference's ServiceRequest/Response
+  trace_cases.npz       outputs of the reference's data_generator/trace_generator.py
+                        (trace_generate_lru, seeded python + numpy streams) and
+                        trace_profile.py (trace_profile) for small cases
 """
 import json
 import os
@@ -25,6 +28,8 @@ REF = "/root/reference"
 sys.path.insert(0, REF)
 
 from data_generator.dlrm_data_caffe2 import DLRMDataGenerator  # noqa: E402  (reference)
+from data_generator import trace_generator as ref_tracegen      # noqa: E402  (reference)
+from data_generator import trace_profile as ref_traceprof       # noqa: E402  (reference)
 from utils import packets as ref_packets                       # noqa: E402  (reference)
 from utils.utils import cli as ref_cli                         # noqa: E402  (reference)
 
@@ -68,6 +73,55 @@ DATAGEN_CASES = {
                       "--arch_mlp_bot", "3-4", "--arch_mlp_top", "8-1", "--num_indices_per_lookup", "2",
                       "--num_batches", "1", "--max_mini_batch_size", "6", "--round_targets", "True"],
 }
+
+
+# name -> (table_size, list_sd, probabilities, trace length, enable_padding, seed)
+TRACE_CASES = {
+    "mostly_new": (400, [0, 3, 7, 20], [0.9, 0.05, 0.03, 0.02], 300, False, 11),
+    "high_reuse": (500, [0, 1, 2, 3, 5, 8, 13, 40, 100],
+                   [0.3, 0.2, 0.1, 0.1, 0.1, 0.05, 0.05, 0.05, 0.05], 4000, False, 7),
+    "high_reuse_padded": (500, [0, 1, 2, 3, 5, 8, 13, 40, 100],
+                          [0.3, 0.2, 0.1, 0.1, 0.1, 0.05, 0.05, 0.05, 0.05], 4000, True, 7),
+    "table_exhausted": (150, [0, 1, 2, 5, 30], [0.5, 0.2, 0.1, 0.1, 0.1], 2000, False, 3),
+}
+# name -> (ids in [0, hi), trace length, max_stack_distance, seed)
+PROFILE_CASES = {
+    "narrow_window": (50, 1500, 20, 5),
+    "wide_window": (30, 1000, 5000, 6),
+    "window_one": (5, 300, 1, 8),
+    "sparse_reuse": (400, 1500, 100, 9),
+}
+
+
+def cumulative(probs):
+    c, acc = [], 0.0
+    for p in probs:
+        acc += p
+        c.append(acc)
+    c[-1] = 1.0
+    return c
+
+
+def trace_goldens():
+    import random
+    arrays = {}
+    for name, (rows, list_sd, probs, k, pad, seed) in TRACE_CASES.items():
+        cumm = cumulative(probs)
+        random.seed(seed)
+        np.random.seed(seed)
+        tr = ref_tracegen.trace_generate_lru(rows, list_sd, cumm, k, pad)
+        arrays["gen/%s/params" % name] = np.array([rows, k, int(pad), seed], dtype=np.int64)
+        arrays["gen/%s/list_sd" % name] = np.array(list_sd, dtype=np.int64)
+        arrays["gen/%s/cumm_sd" % name] = np.array(cumm, dtype=np.float64)
+        arrays["gen/%s/trace" % name] = np.array(tr, dtype=np.uint64)
+        arrays["gen/%s/rng_tail" % name] = np.random.random_sample(2)
+    for name, (hi, n, window, seed) in PROFILE_CASES.items():
+        tr = np.random.RandomState(seed).randint(0, hi, n).astype(np.int32)
+        sd, la = ref_traceprof.trace_profile(tr, window)
+        arrays["prof/%s/params" % name] = np.array([hi, n, window, seed], dtype=np.int64)
+        arrays["prof/%s/stack_distances" % name] = np.array(sd, dtype=np.int64)
+        arrays["prof/%s/line_accesses" % name] = np.array(la, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "trace_cases.npz"), **arrays)
 
 
 def run_ref_cli(argv):
@@ -123,6 +177,7 @@ def main():
     with open(os.path.join(HERE, "packets.json"), "w") as f:
         json.dump({"ServiceRequest": sorted(vars(req)), "ServiceResponse": sorted(vars(resp))},
                   f, indent=1)
+    trace_goldens()
     print("golden fixtures written to", HERE)
 
 

@@ -69,10 +69,10 @@ class Case(object):
     pass
 
 
-def make_case(name, num_batches=2, max_batch=64, seed=123):
+def make_case(name, num_batches=2, max_batch=64, seed=123, extra=()):
     argv = list(SMALL[name]) + ["--num_batches", str(num_batches),
                                 "--max_mini_batch_size", str(max_batch),
-                                "--numpy_rand_seed", str(seed)]
+                                "--numpy_rand_seed", str(seed)] + list(extra)
     c = Case()
     c.name = name
     c.args = cli(argv)                                   # seeds numpy
