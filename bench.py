@@ -68,7 +68,7 @@ def parse_args():
     p.add_argument("--no_e2e", action="store_true")
     p.add_argument("--no_system", action="store_true",
                    help="skip the Poisson-arrival serving run through the Queue API")
-    p.add_argument("--system_rates_ms", type=str, default="0.5,0.125,0.09",
+    p.add_argument("--system_rates_ms", type=str, default="0.5,0.125,0.09,0.06,0.045",
                    help="mean inter-arrival times (ms) of the serving run")
     p.add_argument("--system_queries", type=int, default=2000)
     p.add_argument("--seed", type=int, default=123)

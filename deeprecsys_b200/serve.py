@@ -22,7 +22,6 @@ from __future__ import absolute_import, division, print_function
 import json
 import multiprocessing as mp
 import sys
-import threading
 import time
 
 import numpy as np
@@ -54,18 +53,43 @@ def _sleep_until(t):
         if dt > 0.002:
             time.sleep(dt - 0.001)      # coarse sleep, then spin (loadGenerator.py:57-64 does the same)
         else:
-            time.sleep(0)               # yield the GIL: the Queue feeder thread must get to run,
-                                        # or a put() sits behind this spin for a switch interval
+            time.sleep(0)               # yield the core between polls
+
+
+def _generate_load(args, accel_q, report_q, n_total, warmup_queries, arrival_ms, seed):
+    """Load-generator process (the reference runs loadGenerator() as its own process too,
+    DeepRecSys.py:74-81): Poisson arrivals of ServiceRequests into the bounded accel queue."""
+    from deeprecsys_b200.accelInferenceEngine import _direct_put
+    sys.setswitchinterval(1e-4)
+    put = _direct_put(accel_q)          # same bytes as Queue.put, written without a feeder thread
+    rng = np.random.RandomState(seed)
+    sizes = query_sizes(args, n_total, rng)
+    gaps = rng.exponential(arrival_ms / 1000.0, n_total)
+    nb = max(1, args.num_batches)
+    t_next = time.time()
+    t_first = None
+    for i in range(n_total):
+        t_next += gaps[i]
+        _sleep_until(t_next)
+        req = ServiceRequest(batch_id=i % nb, epoch=i // nb, batch_size=int(sizes[i]), sub_id=0,
+                             total_sub_batches=1, exp_packet=(i < warmup_queries))
+        req.arrival_time = time.time()
+        if i == warmup_queries:
+            t_first = req.arrival_time
+        put(req)                        # blocks when the engine falls behind (bounded queue)
+    report_q.put((t_first, time.time()))
 
 
 class SystemHarness(object):
     """One accel engine process (started once: dataset + parameters are regenerated inside it,
     like every engine process of the reference) driven through the reference's Queue protocol;
-    ``run`` performs one experiment at a fixed mean inter-arrival time."""
+    ``run`` performs one experiment at a fixed mean inter-arrival time.  Process layout as in
+    DeepRecSys.py: the load generator is its own process, this (parent) process only collects
+    responses (DeepRecSys.py:92-123)."""
 
     def __init__(self, args):
         self.args = args
-        ctx = mp.get_context("fork")        # DeepRecSys.py uses the default (fork) start method
+        self.ctx = ctx = mp.get_context("fork")   # DeepRecSys.py uses the default (fork) start method
         self.accel_q = ctx.Queue(maxsize=32)                  # DeepRecSys.py:45
         self.resp_q, self.ready_q = ctx.Queue(), ctx.Queue()
         self.proc = ctx.Process(target=accelInferenceEngine,
@@ -73,46 +97,42 @@ class SystemHarness(object):
         self.proc.daemon = True
         self.proc.start()
         self.ready_q.get()                                    # loadGenerator.py:76-78
-        self.responses = []
-        self.collector = threading.Thread(target=self._collect, daemon=True)
-        self.collector.start()
-        sys.setswitchinterval(1e-4)     # generator, Queue feeder and collector share one GIL
 
-    def _collect(self):
-        while True:
-            r = self.resp_q.get()
-            if r is None:
-                return
-            self.responses.append(r)
-
-    def run(self, n_queries, arrival_ms, seed=0, warmup_queries=20):
-        args = self.args
-        rng = np.random.RandomState(seed)
+    def run(self, n_queries, arrival_ms, seed=0, warmup_queries=20, timeout_s=300.0):
+        import queue as _queue
         n_total = n_queries + warmup_queries
-        sizes = query_sizes(args, n_total, rng)
-        gaps = rng.exponential(arrival_ms / 1000.0, n_total)
-        first = len(self.responses)
-        t_next = time.time()
-        t_first = None
-        for i in range(n_total):
-            t_next += gaps[i]
-            _sleep_until(t_next)
-            req = ServiceRequest(batch_id=i % max(1, args.num_batches),
-                                 epoch=i // max(1, args.num_batches),
-                                 batch_size=int(sizes[i]), sub_id=0, total_sub_batches=1,
-                                 exp_packet=(i < warmup_queries))
-            req.arrival_time = time.time()
-            if i == warmup_queries:
-                t_first = req.arrival_time
-            self.accel_q.put(req)       # blocks when the engine falls behind (bounded queue)
-        deadline = time.time() + 120
-        while len(self.responses) - first < n_total and time.time() < deadline:
-            time.sleep(0.001)
-        got = self.responses[first:]
+        report_q = self.ctx.Queue()
+        gen = self.ctx.Process(target=_generate_load,
+                               args=(self.args, self.accel_q, report_q, n_total, warmup_queries,
+                                     arrival_ms, seed))
+        gen.daemon = True
+        gen.start()
+        got = []
+        deadline = time.time() + timeout_s
+        while len(got) < n_total and time.time() < deadline:
+            try:
+                r = self.resp_q.get(timeout=1.0)
+            except _queue.Empty:
+                if not self.proc.is_alive():
+                    break
+                continue
+            if r is None:
+                break
+            got.append(r)
+        try:
+            t_first, _ = report_q.get(timeout=10.0)
+        except _queue.Empty:
+            t_first = None
+        gen.join(timeout=10)
+        if gen.is_alive():
+            gen.terminate()
         meas = [r for r in got if not r.exp_packet]
+        if not meas or t_first is None:
+            raise RuntimeError("serving run produced %d of %d responses" % (len(got), n_total))
         lat = np.array([r.inference_end_time - r.arrival_time for r in meas]) * 1e3
         items = int(sum(r.batch_size for r in meas))
         failed = sum(1 for r in meas if r.out_batch_size != r.batch_size)
+        failed += n_queries - len(meas)
         span = max(r.inference_end_time for r in meas) - t_first
         return {
             "arrival_ms": arrival_ms, "queries": len(meas), "failed": failed, "items": items,
@@ -124,8 +144,16 @@ class SystemHarness(object):
         }
 
     def close(self):
+        import queue as _queue
         self.accel_q.put(None)
-        self.collector.join(timeout=120)
+        deadline = time.time() + 120
+        while time.time() < deadline:
+            try:
+                if self.resp_q.get(timeout=1.0) is None:
+                    break
+            except _queue.Empty:
+                if not self.proc.is_alive():
+                    break
         self.proc.join(timeout=60)
         if self.proc.is_alive():
             self.proc.terminate()

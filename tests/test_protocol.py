@@ -299,3 +299,51 @@ def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_pat
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
     log = (stage / "log" / "out.log").read_text()
     assert "'consumer_id': 1" in log          # accel engine = last engine slot
+
+
+def test_direct_response_writes_are_plain_queue_traffic():
+    """_direct_put writes the bytes Queue.put's feeder thread would write: a stock get() on the
+    other side sees the objects in order, the bounded-queue accounting holds (maxsize blocks the
+    writer, get() frees a slot), several processes may share one queue, and a burst far larger
+    than the pipe's capacity neither deadlocks nor reorders."""
+    ctx = mp.get_context("fork")
+    q = ctx.Queue(maxsize=4)
+    put = accel_mod._direct_put(q)
+    for i in range(4):
+        put(("x", i))
+    assert q.full()
+    assert [q.get(timeout=5) for _ in range(4)] == [("x", i) for i in range(4)]
+    assert q.empty()
+
+    big = ctx.Queue()
+
+    def writer(tag, n):
+        w = accel_mod._direct_put(big)
+        for i in range(n):
+            w((tag, i, "p" * 300))
+
+    procs = [ctx.Process(target=writer, args=(t, 3000)) for t in ("a", "b")]
+    for p in procs:
+        p.start()
+    time.sleep(0.3)                                # writers fill the 64 KB pipe and block
+    seen = {"a": [], "b": []}
+    for _ in range(6000):
+        tag, i, _pad = big.get(timeout=30)
+        seen[tag].append(i)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert seen["a"] == list(range(3000)) and seen["b"] == list(range(3000))
+    # a queue whose feeder thread already runs keeps using it (ordering), as does a non-Queue
+    started = ctx.Queue()
+    started.put(1)
+    assert accel_mod._direct_put(started) == started.put
+    import queue as _q
+    plain = _q.Queue()
+    assert accel_mod._direct_put(plain) == plain.put
+    os.environ["DRS_ACCEL_QUEUE_FEEDER"] = "1"
+    try:
+        fresh = ctx.Queue()
+        assert accel_mod._direct_put(fresh) == fresh.put
+    finally:
+        del os.environ["DRS_ACCEL_QUEUE_FEEDER"]
