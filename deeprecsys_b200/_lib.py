@@ -20,7 +20,7 @@ MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE, MLP_RNN_BASE = 0, 1, 
 (STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS, STAGE_TASK,
  STAGE_IDS) = range(8)
 SHARD_TABLE, SHARD_ROW = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 SHARD_BLOB_BYTES = 192
 
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
@@ -96,6 +96,8 @@ _SIGNATURES = {
                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "drs_host_alloc": (C.c_int, [_PP, C.c_int64]),
     "drs_host_free": (C.c_int, [C.c_void_p]),
+    "drs_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "drs_host_unregister": (C.c_int, [C.c_void_p]),
     "drs_shard_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "drs_shard_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }

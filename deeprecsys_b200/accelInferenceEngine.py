@@ -123,7 +123,8 @@ class AccelBackend(object):
     def depth(self):
         return self.engine.lane_count()
 
-    def submit(self, batch_id, batch_size):
+    def _next_out(self):
+        import ctypes
         if not hasattr(self, "_out_pool"):
             from deeprecsys_b200.engine import pinned_empty
             self._out_pool = [pinned_empty((int(self.args.max_mini_batch_size), self.spec.out_dim),
@@ -131,8 +132,10 @@ class AccelBackend(object):
             self._out_next = 0
         buf, _owner = self._out_pool[self._out_next]
         self._out_next = (self._out_next + 1) % len(self._out_pool)
-        import ctypes
-        out_ptr = ctypes.c_void_p(buf.ctypes.data)
+        return buf, ctypes.c_void_p(buf.ctypes.data)
+
+    def submit(self, batch_id, batch_size):
+        buf, out_ptr = self._next_out()
         if self.upload:                    # H2D of this packet's inputs from the pinned dataset
             p = self._pinned[batch_id]
             ticket = self.engine.submit_host(p["dense_ptr"], p["ids_ptrs"], 0, p["len_ptrs"],
@@ -141,15 +144,73 @@ class AccelBackend(object):
             ticket = self.engine.submit_staged(batch_id, int(batch_size), out_ptr)
         return ("ticket", ticket, buf, int(batch_size))
 
+    # requests that bring their own tensors (utils.packets.TensorServiceRequest) ----------------
+    def _attach_ring(self, desc):
+        """Map a producer's shared-memory ring once and page-lock it, so that the H2D copies of
+        its slots are asynchronous DMA straight from the producer's bytes."""
+        from deeprecsys_b200.utils.input_ring import SharedInputRing
+        if not hasattr(self, "_rings"):
+            self._rings = {}
+        ring = self._rings.get(desc["path"])
+        if ring is None:
+            ring = SharedInputRing.attach(desc)
+            if ring.T != self.spec.T or ring.m_den != self.spec.m_den:
+                raise ValueError("ring %s is laid out for %d tables / %d dense features, the model "
+                                 "has %d / %d" % (desc["path"], ring.T, ring.m_den, self.spec.T,
+                                                  self.spec.m_den))
+            try:
+                from deeprecsys_b200 import _lib
+                _lib.check(self.engine.lib.drs_host_register(ring.base_address(), ring.nbytes))
+                ring.registered = True
+            except Exception as exc:       # pageable memory still works: the driver stages it
+                print("[Accel] ring %s not page-locked (%r); copies will be staged"
+                      % (desc["path"], exc))
+            ring._ptr_cache = {}
+            self._rings[desc["path"]] = ring
+        return ring
+
+    def submit_inputs(self, request):
+        import ctypes
+        B, T = int(request.batch_size), self.spec.T
+        buf, out_ptr = self._next_out()
+        if request.ring is not None:
+            ring = self._attach_ring(request.ring)
+            ptrs = ring._ptr_cache.get(request.slot)
+            if ptrs is None:
+                d, i, l = ring.pointers(request.slot)
+                ptrs = (ctypes.c_void_p(d) if d is not None else None,
+                        (ctypes.c_void_p * T)(*i), (ctypes.c_void_p * T)(*l))
+                ring._ptr_cache[request.slot] = ptrs
+            ticket = self.engine.submit_host(ptrs[0], ptrs[1], 0, ptrs[2], B, out_ptr)
+            return ("ticket", ticket, buf, B)
+        dense, dptr, ids, is64, lengths = self.engine._prep(request.dense, request.ids,
+                                                            request.lengths, B)
+        ticket = self.engine.submit_host(
+            dptr, (ctypes.c_void_p * T)(*[a.ctypes.data for a in ids]), is64,
+            (ctypes.c_void_p * T)(*[a.ctypes.data for a in lengths]), B, out_ptr)
+        return ("ticket", ticket, buf, B, (dense, ids, lengths))     # arrays alive until complete
+
+    def serve_inputs(self, request):
+        return self.complete(self.submit_inputs(request))
+
     def complete(self, handle):
         if handle[0] == "done":
             return handle[1]
-        _, ticket, buf, B = handle
+        ticket, buf, B = handle[1:4]
         self.engine.wait(ticket)
         return buf[:B]
 
     def close(self):
+        for ring in getattr(self, "_rings", {}).values():
+            if ring.registered:
+                self.engine.lib.drs_host_unregister(ring.base_address())
+            ring.close()
         self.engine.close()
+
+
+def _carries_inputs(request):
+    has = getattr(request, "has_inputs", None)
+    return bool(has and has())
 
 
 # tests replace this with an oracle-backed fake (no GPU in the authoring container)
@@ -367,9 +428,13 @@ def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, si
         try:
             if pipelined:
                 inflight.append((request, start_time,
-                                 backend.submit(request.batch_id, request.batch_size)))
+                                 backend.submit_inputs(request) if _carries_inputs(request)
+                                 else backend.submit(request.batch_id, request.batch_size)))
                 continue
-            out = backend.serve(request.batch_id, request.batch_size)
+            if _carries_inputs(request):
+                out = backend.serve_inputs(request)
+            else:
+                out = backend.serve(request.batch_id, request.batch_size)
             out_batch_size = int(out.shape[0])
             if backend.dump_dir:
                 np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (

@@ -1052,6 +1052,17 @@ int drs_host_free(void* ptr) {
   return DRS_OK;
 }
 
+int drs_host_register(void* ptr, int64_t bytes) {
+  CHECK_ARG(ptr && bytes > 0, "bad arguments");
+  CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return DRS_OK;
+}
+
+int drs_host_unregister(void* ptr) {
+  if (ptr) CU(cudaHostUnregister(ptr));
+  return DRS_OK;
+}
+
 int drs_create(const drs_spec* spec, int device, drs_engine** out) {
   CHECK_ARG(spec && out, "spec/out is NULL");
   CHECK_ARG(spec->n_tables >= 1 && spec->table_rows, "need at least one embedding table");

@@ -10,6 +10,8 @@ keyword is stored as ``queue_start_time``.
 
 Packets carry no tensors: a request names a pre-generated
 batch by ``batch_id`` and asks for its first ``batch_size`` rows.
+``TensorServiceRequest`` is this backend's extension for queries that bring
+their own inputs; the reference classes stay as they are.
 """
 
 _REQUEST_FIELDS = ("batch_id", "batch_size", "epoch", "arrival_time",
@@ -30,6 +32,30 @@ class ServiceRequest(object):
         # The reference's __str__ raises (str + tuple); this one works.
         return "Request[%s] -> arrival_time %s" % (
             (self.epoch, self.batch_id, self.batch_size), self.arrival_time)
+
+
+class TensorServiceRequest(ServiceRequest):
+    """A request that carries its own inputs instead of naming a pre-generated batch.
+
+    Not in the reference (its packets only name ``batch_id``/``batch_size``,
+    utils/packets.py:6-22): an engine that really computes can serve data the client sends.
+    Every reference attribute is kept — the orchestrator joins and logs by them — and one of two
+    payloads is added:
+      * ``ring`` + ``slot`` + ``counts``: the tensors sit in slot ``slot`` of the shared-memory
+        ring described by ``ring`` (utils/input_ring.py); ``counts[t]`` = ids of table t;
+      * ``dense`` / ``ids`` / ``lengths``: the arrays themselves, pickled with the request
+        (simple, slow for large queries).
+    The CPU engines of the reference ignore the extra attributes and serve the request from
+    ``batch_id`` as before."""
+
+    def __init__(self, dense=None, ids=None, lengths=None, ring=None, slot=None, counts=None,
+                 **reference_fields):
+        super(TensorServiceRequest, self).__init__(**reference_fields)
+        self.dense, self.ids, self.lengths = dense, ids, lengths
+        self.ring, self.slot, self.counts = ring, slot, counts
+
+    def has_inputs(self):
+        return self.ring is not None or self.ids is not None
 
 
 class ServiceResponse(object):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRS_ABI_VERSION 4
+#define DRS_ABI_VERSION 5
 
 /* status codes */
 enum {
@@ -215,6 +215,12 @@ int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms
 /* Pinned host memory for the upload path (so H2D/D2H are true async DMA). */
 int drs_host_alloc(void** ptr, int64_t bytes);
 int drs_host_free(void* ptr);
+/* Page-lock memory the caller already owns — e.g. a shared-memory ring another process writes
+ * query tensors into (deeprecsys_b200/utils/input_ring.py) — so that drs_submit_host /
+ * drs_enqueue_host copy from it by asynchronous DMA.  Optional: unregistered (pageable) buffers
+ * are accepted by every entry point, the copy is then staged by the driver. */
+int drs_host_register(void* ptr, int64_t bytes);
+int drs_host_unregister(void* ptr);
 
 /* Multi-GPU, one process per GPU.
  * Row-wise sharding (spec.shard_mode = DRS_SHARD_ROW): connect first, then drs_load_table with

@@ -46,6 +46,26 @@ class OracleBackend(object):
         dense = d if self.spec.m_den > 0 else None
         return self.model.forward(dense, list(i), list(l)).numpy()
 
+    def serve_inputs(self, request):
+        """A TensorServiceRequest: the inputs come with the request (inline arrays or a slot of
+        a shared-memory ring) instead of from the pre-generated dataset."""
+        import torch
+        B = int(request.batch_size)
+        if request.ring is not None:
+            from deeprecsys_b200.utils.input_ring import SharedInputRing
+            if not hasattr(self, "_rings"):
+                self._rings = {}
+            ring = self._rings.get(request.ring["path"])
+            if ring is None:
+                ring = self._rings[request.ring["path"]] = SharedInputRing.attach(request.ring)
+            dense, ids, lengths = ring.read(request.slot, B, request.counts)
+        else:
+            dense, ids, lengths = request.dense, request.ids, request.lengths
+        dense = np.array(dense[:B]) if self.spec.m_den > 0 else None
+        ids = [torch.as_tensor(np.array(i), dtype=torch.int64) for i in ids]
+        lengths = [np.array(l[:B], dtype=np.int32) for l in lengths]
+        return self.model.forward(dense, ids, lengths).numpy()
+
     def close(self):
         pass
 
