@@ -236,14 +236,18 @@ def _direct_put(q):
     try:
         from multiprocessing.reduction import ForkingPickler
         sem, writer, wlock = q._sem, q._writer, q._wlock
-        send_bytes, dumps = writer.send_bytes, ForkingPickler.dumps
+        import pickle
+        send_bytes, dumps, plain_dumps = writer.send_bytes, ForkingPickler.dumps, pickle.dumps
         if getattr(q, "_thread", None) is not None or getattr(q, "_joincancelled", None) is None:
             return q.put                   # feeder already running (order!) / not a stock Queue
     except AttributeError:
         return q.put
 
     def put(obj):
-        data = dumps(obj)
+        try:
+            data = plain_dumps(obj)        # packets are plain python objects: no need to build a
+        except Exception:                  # ForkingPickler (a Pickler + dispatch table) per call
+            data = dumps(obj)
         sem.acquire()
         if wlock is None:
             send_bytes(data)
@@ -251,6 +255,20 @@ def _direct_put(q):
             with wlock:
                 send_bytes(data)
     return put
+
+
+def _readable_probe(q):
+    """``probe() -> bool``: is a packet waiting on this queue's pipe?  ``Queue.get(block=False)``
+    answers the same question through ``connection.wait`` (a selector object built, registered
+    and torn down per call: ~10 us of the ~50 us a packet costs the serving loop); a ``poll``
+    object registered once answers in about one.  None when the queue is not a stock Queue."""
+    try:
+        import select
+        poller = select.poll()
+        poller.register(q._reader.fileno(), select.POLLIN)
+    except (AttributeError, OSError, ValueError):
+        return None
+    return lambda: bool(poller.poll(0))
 
 
 def _die_with_parent():
@@ -317,6 +335,23 @@ def accelInferenceEngine(args,
 
 
 def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):
+    """DRS_ACCEL_PROFILE=<file>: run the serve loop under cProfile and write the hottest
+    functions there when the engine exits (where a packet's host time goes)."""
+    prof_path = os.environ.get("DRS_ACCEL_PROFILE")
+    if not prof_path:
+        return _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibling)
+    import cProfile
+    import pstats
+    prof = cProfile.Profile()
+    try:
+        return prof.runcall(_engine_loop, args, requestQueue, engine_id, responseQueue,
+                            readyQueue, sibling)
+    finally:
+        with open(prof_path + (".%d" % os.getpid() if sibling else ""), "w") as f:
+            pstats.Stats(prof, stream=f).sort_stats("tottime").print_stats(40)
+
+
+def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):
     np.random.seed(args.numpy_rand_seed)
     np.set_printoptions(precision=args.print_precision)
 
@@ -385,6 +420,7 @@ def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, si
         put_response(response)
 
     multi = sibling or bool(siblings)
+    request_waiting = _readable_probe(requestQueue)
     import queue as _queue
     while True:
         if len(inflight) >= depth:
@@ -395,11 +431,17 @@ def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, si
             # never block on the queue while a packet is in flight: with sibling processes on
             # the same queue a request seen by empty() may be taken by somebody else, and the
             # in-flight packet's response would wait for the next arrival
-            try:
-                request = requestQueue.get(block=False)
-            except _queue.Empty:
-                finish_oldest()
-                continue
+            if request_waiting is not None and not multi:
+                if not request_waiting():  # sole consumer: a readable pipe holds a whole packet
+                    finish_oldest()
+                    continue
+                request = requestQueue.get()
+            else:
+                try:
+                    request = requestQueue.get(block=False)
+                except _queue.Empty:
+                    finish_oldest()
+                    continue
         else:
             request = requestQueue.get()
         debugPrint(args, "Accel", "Pulled request")

@@ -116,79 +116,90 @@ def test_tensor_request_keeps_the_reference_fields_and_stays_small():
     assert slots_needed(32, 3) == 37
 
 
-def _serve_through_engine(requests, tmp_path):
-    from oracle.cpu_inference_engine import OracleBackend    # CPU test tier only: no GPU here
-    args = cli(SMALL_SYSTEM)
-    dump = tmp_path / "dump"
-    dump.mkdir()
-    os.environ["DRS_ACCEL_DUMP_DIR"] = str(dump)
-    ctx = mp.get_context("fork")
-    rq, resp, ready = ctx.Queue(), ctx.Queue(), ctx.Queue()
-    old = accel_mod.BACKEND_FACTORY
-    accel_mod.BACKEND_FACTORY = OracleBackend
-    try:
-        p = ctx.Process(target=accel_mod.accelInferenceEngine, args=(args, rq, 1, resp, ready))
-        p.daemon = True
-        p.start()
-    finally:
-        accel_mod.BACKEND_FACTORY = old
-        del os.environ["DRS_ACCEL_DUMP_DIR"]
-    assert ready.get(timeout=120) is True
-    for r in requests:
-        rq.put(r)
-    rq.put(None)
-    out = []
-    while True:
-        item = resp.get(timeout=120)
-        if item is None:
-            break
-        out.append(item)
-    p.join(timeout=30)
-    dumps = {os.path.basename(f): np.load(f) for f in glob.glob(str(dump / "*.npy"))}
-    return args, out, dumps
+ENGINE_SCRIPT = r"""
+import glob, multiprocessing as mp, os, pickle, sys
+import numpy as np
+from deeprecsys_b200 import accelInferenceEngine as accel_mod
+from deeprecsys_b200.utils.input_ring import SharedInputRing
+from deeprecsys_b200.utils.packets import ServiceRequest, TensorServiceRequest
+from deeprecsys_b200.utils.utils import cli
+from oracle.cpu_inference_engine import OracleBackend        # CPU test tier only: no GPU here
+from tests.test_input_ring import SMALL_SYSTEM, _query
+
+out_dir = sys.argv[1]
+rng = np.random.RandomState(42)
+ring = SharedInputRing.create(n_slots=4, n_tables=4, m_den=13, max_batch=64, max_lookups=640)
+fields = dict(sub_id=0, total_sub_batches=1, exp_packet=False, arrival_time=0.0)
+queries, requests = {}, []
+for n, (B, ragged) in enumerate([(64, False), (9, True), (1, False)]):
+    d, i, l = _query(rng, B, ragged)
+    counts = ring.write(n, d, i, l, B)
+    queries[(10 + n, 0, B)] = (d, i, l)
+    requests.append(TensorServiceRequest(ring=ring.descriptor(), slot=n, counts=counts,
+                                         batch_id=0, epoch=10 + n, batch_size=B, **fields))
+d, i, l = _query(rng, 5, True)
+queries[(20, 1, 5)] = (d, i, l)
+requests.append(TensorServiceRequest(dense=d, ids=i, lengths=l, batch_id=1, epoch=20,
+                                     batch_size=5, **fields))
+requests.append(ServiceRequest(batch_id=1, epoch=30, batch_size=6, **fields))
+requests.append(TensorServiceRequest(ring=dict(ring.descriptor(), path=ring.path + ".gone"),
+                                     slot=0, counts=[0] * 4, batch_id=0, epoch=40, batch_size=3,
+                                     **fields))
+os.environ["DRS_ACCEL_DUMP_DIR"] = out_dir
+accel_mod.BACKEND_FACTORY = OracleBackend
+ctx = mp.get_context("fork")
+rq, resp, ready = ctx.Queue(), ctx.Queue(), ctx.Queue()
+p = ctx.Process(target=accel_mod.accelInferenceEngine, args=(cli(SMALL_SYSTEM), rq, 1, resp, ready))
+p.daemon = True
+p.start()
+assert ready.get(timeout=120) is True
+for r in requests:
+    rq.put(r)
+rq.put(None)
+responses = []
+while True:
+    item = resp.get(timeout=120)
+    if item is None:
+        break
+    responses.append((item.epoch, item.batch_size, item.out_batch_size))
+p.join(timeout=30)
+ring.close()
+with open(os.path.join(out_dir, "run.pkl"), "wb") as f:
+    pickle.dump({"responses": responses, "queries": queries,
+                 "sent": [(q.epoch, q.batch_size) for q in requests]}, f)
+"""
 
 
 def test_engine_serves_requests_that_carry_inputs(tmp_path):
     """Ring-backed, inline and plain (batch_id) requests through one engine process: each
     response answers its request, and the outputs are what the oracle computes for THOSE
-    inputs (which differ from the pre-generated dataset)."""
+    inputs (which differ from the pre-generated dataset).  Run in a fresh interpreter: the
+    engine process is forked, and a child forked from this (multi-threaded, torch-using) pytest
+    process can deadlock in torch's thread pool."""
+    import subprocess
+    import sys
     from deeprecsys_b200.spec import ModelSpec, draw_all_parameters
     from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
     from oracle import numpy_oracle as O
-    rng = np.random.RandomState(42)
-    ring = SharedInputRing.create(n_slots=4, n_tables=4, m_den=13, max_batch=64, max_lookups=640)
-    try:
-        fields = dict(sub_id=0, total_sub_batches=1, exp_packet=False, arrival_time=0.0)
-        queries, requests = {}, []
-        for n, (B, ragged) in enumerate([(64, False), (9, True), (1, False)]):
-            d, i, l = _query(rng, B, ragged)
-            counts = ring.write(n, d, i, l, B)
-            queries[(10 + n, B)] = (d, i, l)
-            requests.append(TensorServiceRequest(ring=ring.descriptor(), slot=n, counts=counts,
-                                                 batch_id=0, epoch=10 + n, batch_size=B, **fields))
-        d, i, l = _query(rng, 5, True)
-        queries[(20, 5)] = (d, i, l)
-        requests.append(TensorServiceRequest(dense=d, ids=i, lengths=l, batch_id=1, epoch=20,
-                                             batch_size=5, **fields))
-        requests.append(ServiceRequest(batch_id=1, epoch=30, batch_size=6, **fields))
-        bad = TensorServiceRequest(ring=dict(ring.descriptor(), path=ring.path + ".gone"), slot=0,
-                                   counts=[0] * 4, batch_id=0, epoch=40, batch_size=3, **fields)
-        requests.append(bad)
-        args, responses, dumps = _serve_through_engine(requests, tmp_path)
-    finally:
-        ring.close()
-    assert [(r.epoch, r.batch_size) for r in responses] == [(q.epoch, q.batch_size)
-                                                            for q in requests]
-    assert [r.out_batch_size for r in responses] == [64, 9, 1, 5, 6, 0]    # bad ring: answered, 0
-    # the engine process drew the parameters from the seed; redo it here for the oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, "-c", ENGINE_SCRIPT, str(tmp_path)], cwd=root,
+                          env=dict(os.environ, PYTHONPATH=root, PYTHONWARNINGS="ignore"),
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    with open(str(tmp_path / "run.pkl"), "rb") as f:
+        run = pickle.load(f)
+    dumps = {os.path.basename(f): np.load(f) for f in glob.glob(str(tmp_path / "*.npy"))}
+    assert [r[:2] for r in run["responses"]] == run["sent"]
+    assert [r[2] for r in run["responses"]] == [64, 9, 1, 5, 6, 0]    # bad ring: answered, 0
+    # the engine process drew the dataset and the parameters from the seed; redo it here
     args = cli(SMALL_SYSTEM)
     gen = DLRMDataGenerator(args)
     _, lX, lS_l, lS_i = gen.generate_input_data()
     gen.generate_output_data()
     spec = ModelSpec(args)
     tables, fcs = draw_all_parameters(spec)
-    for (epoch, B), (d, i, l) in queries.items():
-        got = dumps["accel_e%d_b%d_n%d.npy" % (epoch, 0 if epoch < 20 else 1, B)]
+    for (epoch, batch_id, B), (d, i, l) in run["queries"].items():
+        got = dumps["accel_e%d_b%d_n%d.npy" % (epoch, batch_id, B)]
         want = O.forward(spec, tables, fcs, d, i, l)["out"]
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
     plain = O.forward(spec, tables, fcs, lX[1][:6], [x[:60] for x in lS_i[1]],
