@@ -347,3 +347,43 @@ def test_direct_response_writes_are_plain_queue_traffic():
         assert accel_mod._direct_put(fresh) == fresh.put
     finally:
         del os.environ["DRS_ACCEL_QUEUE_FEEDER"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+def test_reference_scheduler_tunes_against_our_engine(tmp_path):
+    """the reference's hill-climbing schedulers (scheduler.py, driven by
+    loadGenerator.py with --tune_batch_qps --tune_accel_qps) run unmodified on top of this
+    engine: they settle on a sub-batch size and an accel_request_size_thres from the latencies
+    the engine processes really produce, discard queued requests while switching configurations
+    (scheduler.py:158-169 — responses need not match the generator's counters), and the run
+    terminates with every engine joined."""
+    stage = tmp_path / "drs"
+    stage.mkdir()
+    for name in ["DeepRecSys.py", "loadGenerator.py", "scheduler.py", "utils"]:
+        os.symlink(os.path.join(REF, name), stage / name)
+    (stage / "inferenceEngine.py").write_text(SHIM_CPU)
+    (stage / "accelInferenceEngine.py").write_text(textwrap.dedent(SHIM_ACCEL))
+    argv = SMALL_SYSTEM + ["--queue", "--model_accel", "--inference_engines", "2",
+                           "--nepochs", "3", "--batch_size_distribution", "normal",
+                           "--avg_mini_batch_size", "32", "--var_mini_batch_size", "16",
+                           "--sub_task_batch_size", "16", "--accel_request_size_thres", "32",
+                           "--avg_arrival_rate", "3", "--log_file", "log/out.log",
+                           "--tune_batch_qps", "--tune_accel_qps", "--sched_timeout", "3",
+                           "--arr_steps", "4", "--req_granularity", "8",
+                           "--batch_configs", "16-32", "--accel_configs", "16-32",
+                           "--min_arr_range", "1", "--max_arr_range", "8",
+                           "--target_latency", "50"]
+    launcher = ("import sys, runpy; sys.path.insert(0, '.'); sys.argv = ['DeepRecSys.py'] + %r; "
+                "runpy.run_path('DeepRecSys.py', run_name='__main__')" % (argv,))
+    proc = subprocess.run([sys.executable, "-c", launcher], cwd=str(stage),
+                          env=dict(os.environ, PYTHONPATH=ROOT, PYTHONWARNINGS="ignore"),
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    out = proc.stdout
+    assert proc.returncode == 0, out[-3000:]
+    assert "Finished batch size scheduler" in out and "Starting accel scheduler" in out
+    assert "Optimal accel configuration" in out, out[-3000:]
+    assert "Scheduler's Optimal accel_size configuration" in out
+    assert "Joined  3  inference engines" in out          # 2 CPU engines + the accel slot
+    assert "Measured p99 tail-latency" in out
+    line = [l for l in out.splitlines() if l.startswith("Accel requests")][0]
+    assert int(line.split()[2]) > 0
