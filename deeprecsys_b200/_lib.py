@@ -12,7 +12,7 @@ import os
 from . import build as _build
 
 # enums of drs_b200.h
-OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_COMM = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_COMM, ERR_HOST = range(7)
 MODEL_DLRM, MODEL_WND, MODEL_NCF, MODEL_DIN, MODEL_MTWND, MODEL_DIEN = range(6)
 INTERACT_CAT, INTERACT_DOT = 0, 1
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2

@@ -59,6 +59,19 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// No C++ exception may cross the C boundary (ctypes / cgo / JNI callers cannot unwind it: the
+// process would abort).  Every entry point is a function-try-block ending in DRS_CATCH.
+static int fail_exception(const char* what) noexcept {
+  try {
+    g_last_error = std::string("C++ exception in libdrs_b200: ") + (what ? what : "unknown");
+  } catch (...) {                      // out of memory while reporting out of memory
+  }
+  return DRS_ERR_HOST;
+}
+#define DRS_CATCH                                                        \
+  catch (const std::exception& ex__) { return fail_exception(ex__.what()); } \
+  catch (...) { return fail_exception(nullptr); }
+
 #define CU(call)                                                                              \
   do {                                                                                        \
     cudaError_t err__ = (call);                                                               \
@@ -1019,13 +1032,13 @@ extern "C" {
 const char* drs_last_error(void) { return g_last_error.c_str(); }
 int drs_abi_version(void) { return DRS_ABI_VERSION; }
 
-int drs_device_count(int* n_out) {
+int drs_device_count(int* n_out) try {
   CHECK_ARG(n_out, "n_out is NULL");
   CU(cudaGetDeviceCount(n_out));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_device_numa_node(int device, int* node_out) {
+int drs_device_numa_node(int device, int* node_out) try {
   CHECK_ARG(node_out, "node_out is NULL");
   *node_out = -1;
   char bus[32] = {0};
@@ -1039,31 +1052,31 @@ int drs_device_numa_node(int device, int* node_out) {
     fclose(f);
   }
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_host_alloc(void** ptr, int64_t bytes) {
+int drs_host_alloc(void** ptr, int64_t bytes) try {
   CHECK_ARG(ptr && bytes >= 0, "bad arguments");
   CU(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 16), cudaHostAllocDefault));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_host_free(void* ptr) {
+int drs_host_free(void* ptr) try {
   if (ptr) CU(cudaFreeHost(ptr));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_host_register(void* ptr, int64_t bytes) {
+int drs_host_register(void* ptr, int64_t bytes) try {
   CHECK_ARG(ptr && bytes > 0, "bad arguments");
   CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_host_unregister(void* ptr) {
+int drs_host_unregister(void* ptr) try {
   if (ptr) CU(cudaHostUnregister(ptr));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_create(const drs_spec* spec, int device, drs_engine** out) {
+int drs_create(const drs_spec* spec, int device, drs_engine** out) try {
   CHECK_ARG(spec && out, "spec/out is NULL");
   CHECK_ARG(spec->n_tables >= 1 && spec->table_rows, "need at least one embedding table");
   CHECK_ARG(spec->emb_dim >= 1, "emb_dim must be >= 1");
@@ -1325,9 +1338,9 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) {
 #undef TRYB
 #undef CHECKB
 #undef CUB
-}
+} DRS_CATCH
 
-int drs_destroy(drs_engine* e) {
+int drs_destroy(drs_engine* e) try {
   if (!e) return DRS_OK;
   cudaSetDevice(e->device);
   for (int i = 0; i < e->n_lanes; ++i)
@@ -1357,15 +1370,15 @@ int drs_destroy(drs_engine* e) {
   for (auto& v : e->prof_ev) cudaEventDestroy(v);
   delete e;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_out_dim(const drs_engine* e, int* out_dim) {
+int drs_out_dim(const drs_engine* e, int* out_dim) try {
   CHECK_ARG(e && out_dim, "NULL argument");
   *out_dim = e->out_dim;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_load_table(drs_engine* e, int table, const float* rows, int64_t n_rows, int dim) {
+int drs_load_table(drs_engine* e, int table, const float* rows, int64_t n_rows, int dim) try {
   CHECK_ARG(e && rows, "NULL argument");
   CHECK_ARG(table >= 0 && table < e->T, "table %d out of range [0,%d)", table, e->T);
   CHECK_ARG(n_rows == e->table_rows[table] && dim == e->D,
@@ -1390,10 +1403,10 @@ int drs_load_table(drs_engine* e, int table, const float* rows, int64_t n_rows, 
   CU(cudaStreamSynchronize(s0(e)));
   e->table_loaded[table] = 1;
   return rewrite_all_descs(e);       // descriptors hold the table pointers
-}
+} DRS_CATCH
 
 int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const float* b, int out_dim,
-                int in_dim) {
+                int in_dim) try {
   CHECK_ARG(e && W && b, "NULL argument");
   CU(cudaSetDevice(e->device));
   Mlp* m = nullptr;
@@ -1437,10 +1450,10 @@ int drs_load_fc(drs_engine* e, int mlp_id, int layer, const float* W, const floa
   CU(cudaStreamSynchronize(s0(e)));
   l.loaded[unit] = 1;
   return DRS_OK;
-}
+} DRS_CATCH
 
 int drs_stage_batch(drs_engine* e, int batch_id, const float* dense, const void* const* idx,
-                    int idx_is_i64, const int32_t* const* lengths, int n_samples) {
+                    int idx_is_i64, const int32_t* const* lengths, int n_samples) try {
   CHECK_ARG(e, "engine is NULL");
   CHECK_ARG(n_samples >= 1, "n_samples must be >= 1");
   CHECK_ARG(idx && lengths, "idx/lengths pointer arrays must not be NULL");
@@ -1480,7 +1493,7 @@ int drs_stage_batch(drs_engine* e, int batch_id, const float* dense, const void*
   if (s.idx64) { cudaFree(s.idx64); s.idx64 = nullptr; }
   e->staged[batch_id] = s;
   return DRS_OK;
-}
+} DRS_CATCH
 
 static int enqueue_staged_on(drs_engine* e, Lane& ln, int batch_id, int batch_size) {
   auto it = e->staged.find(batch_id);
@@ -1494,18 +1507,18 @@ static int enqueue_staged_on(drs_engine* e, Lane& ln, int batch_id, int batch_si
   return enqueue_graph(e, ln, it->second, batch_size);
 }
 
-int drs_enqueue_staged(drs_engine* e, int batch_id, int batch_size) {
+int drs_enqueue_staged(drs_engine* e, int batch_id, int batch_size) try {
   CHECK_ARG(e, "engine is NULL");
   return enqueue_staged_on(e, pick_lane(e), batch_id, batch_size);
-}
+} DRS_CATCH
 
-int drs_sync(drs_engine* e) {
+int drs_sync(drs_engine* e) try {
   CHECK_ARG(e, "engine is NULL");
   CU(cudaSetDevice(e->device));
   return finish_all(e);
-}
+} DRS_CATCH
 
-int drs_infer_staged(drs_engine* e, int batch_id, int batch_size, float* out, drs_timing* tm) {
+int drs_infer_staged(drs_engine* e, int batch_id, int batch_size, float* out, drs_timing* tm) try {
   CHECK_ARG(e, "engine is NULL");
   const auto t0 = std::chrono::steady_clock::now();
   CU(cudaSetDevice(e->device));
@@ -1526,7 +1539,7 @@ int drs_infer_staged(drs_engine* e, int batch_id, int batch_size, float* out, dr
                        .count();
   }
   return DRS_OK;
-}
+} DRS_CATCH
 
 static int enqueue_host_on(drs_engine* e, Lane& ln, const float* dense, const void* const* idx,
                            int idx_is_i64, const int32_t* const* lengths, int batch_size,
@@ -1551,16 +1564,16 @@ static int enqueue_host_on(drs_engine* e, Lane& ln, const float* dense, const vo
 }
 
 int drs_enqueue_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
-                     const int32_t* const* lengths, int batch_size, float* out_pinned) {
+                     const int32_t* const* lengths, int batch_size, float* out_pinned) try {
   CHECK_ARG(e, "engine is NULL");
   Lane& ln = pick_lane(e);
   // the lane's input slot is reused: the previous query on this lane must have been consumed
   CU(cudaStreamSynchronize(ln.stream));
   return enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out_pinned);
-}
+} DRS_CATCH
 
 int drs_infer(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
-              const int32_t* const* lengths, int batch_size, float* out, drs_timing* tm) {
+              const int32_t* const* lengths, int batch_size, float* out, drs_timing* tm) try {
   CHECK_ARG(e, "engine is NULL");
   const auto t0 = std::chrono::steady_clock::now();
   Lane& ln = pick_lane(e);
@@ -1575,13 +1588,13 @@ int drs_infer(drs_engine* e, const float* dense, const void* const* idx, int idx
                        .count();
   }
   return DRS_OK;
-}
+} DRS_CATCH
 
 // Asynchronous submit / wait pair (one submitting thread).  ticket = (sequence << 8) | lane.
 static int64_t make_ticket(drs_engine* e) { return ((++e->submit_seq) << 8) | (int64_t)e->last_lane; }
 
 int drs_submit_staged(drs_engine* e, int batch_id, int batch_size, float* out_pinned,
-                      int64_t* ticket) {
+                      int64_t* ticket) try {
   CHECK_ARG(e && ticket, "NULL argument");
   Lane& ln = pick_lane(e);
   TRY(enqueue_staged_on(e, ln, batch_id, batch_size));
@@ -1590,36 +1603,36 @@ int drs_submit_staged(drs_engine* e, int batch_id, int batch_size, float* out_pi
                        cudaMemcpyDeviceToHost, ln.stream));
   *ticket = make_ticket(e);
   return DRS_OK;
-}
+} DRS_CATCH
 
 int drs_submit_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
                     const int32_t* const* lengths, int batch_size, float* out_pinned,
-                    int64_t* ticket) {
+                    int64_t* ticket) try {
   CHECK_ARG(e && ticket, "NULL argument");
   Lane& ln = pick_lane(e);
   CU(cudaStreamSynchronize(ln.stream));      // the lane's input slot is reused
   TRY(enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out_pinned));
   *ticket = make_ticket(e);
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_wait(drs_engine* e, int64_t ticket) {
+int drs_wait(drs_engine* e, int64_t ticket) try {
   CHECK_ARG(e, "engine is NULL");
   const int lane = (int)(ticket & 0xff);
   CHECK_ARG(lane >= 0 && lane < e->n_lanes, "bad ticket");
   CU(cudaSetDevice(e->device));
   return finish_lane(e, e->lanes[lane]);
-}
+} DRS_CATCH
 
-int drs_lane_count(const drs_engine* e, int* n_lanes) {
+int drs_lane_count(const drs_engine* e, int* n_lanes) try {
   CHECK_ARG(e && n_lanes, "NULL argument");
   *n_lanes = e->n_lanes;
   return DRS_OK;
-}
+} DRS_CATCH
 
 // Stopwatch spanning all lanes: t0 is after everything enqueued so far and before anything
 // enqueued later; t1 is after everything enqueued before the stop.
-int drs_timer_start(drs_engine* e) {
+int drs_timer_start(drs_engine* e) try {
   CHECK_ARG(e, "engine is NULL");
   CU(cudaSetDevice(e->device));
   for (int i = 1; i < e->n_lanes; ++i) {
@@ -1629,9 +1642,9 @@ int drs_timer_start(drs_engine* e) {
   CU(cudaEventRecord(e->ev_timer[0], s0(e)));
   for (int i = 1; i < e->n_lanes; ++i) CU(cudaStreamWaitEvent(e->lanes[i].stream, e->ev_timer[0], 0));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_timer_stop(drs_engine* e, float* elapsed_ms) {
+int drs_timer_stop(drs_engine* e, float* elapsed_ms) try {
   CHECK_ARG(e && elapsed_ms, "NULL argument");
   CU(cudaSetDevice(e->device));
   for (int i = 1; i < e->n_lanes; ++i) {
@@ -1642,10 +1655,10 @@ int drs_timer_stop(drs_engine* e, float* elapsed_ms) {
   CU(cudaEventSynchronize(e->ev_timer[1]));
   CU(cudaEventElapsedTime(elapsed_ms, e->ev_timer[0], e->ev_timer[1]));
   return DRS_OK;
-}
+} DRS_CATCH
 
 int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is_i64,
-                           int64_t n_idx, const int32_t* lengths, int n_segments, float* out) {
+                           int64_t n_idx, const int32_t* lengths, int n_segments, float* out) try {
   CHECK_ARG(e && lengths && out && (idx || n_idx == 0), "NULL argument");
   CHECK_ARG(table >= 0 && table < e->T, "table %d out of range", table);
   CHECK_ARG(n_segments >= 0 && n_idx >= 0, "negative sizes");
@@ -1717,10 +1730,10 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
   cleanup();
   return rc;
 #undef CUC
-}
+} DRS_CATCH
 
 int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap, int* rows,
-                    int* cols) {
+                    int* cols) try {
   CHECK_ARG(e && dst && rows && cols, "NULL argument");
   Lane& ln = e->lanes[e->last_lane];
   CHECK_ARG(ln.last_inputs && ln.last_B > 0, "no query has been served yet");
@@ -1816,21 +1829,21 @@ int drs_fetch_stage(drs_engine* e, int stage, int layer, float* dst, int64_t cap
                     cudaMemcpyDeviceToHost));
   *rows = r; *cols = c;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_launch_count(const drs_engine* e, int64_t* n) {
+int drs_launch_count(const drs_engine* e, int64_t* n) try {
   CHECK_ARG(e && n, "NULL argument");
   *n = e->launches;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_hbm_bytes(const drs_engine* e, int64_t* bytes) {
+int drs_hbm_bytes(const drs_engine* e, int64_t* bytes) try {
   CHECK_ARG(e && bytes, "NULL argument");
   *bytes = e->hbm_bytes;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_profile_begin(drs_engine* e, int max_steps) {
+int drs_profile_begin(drs_engine* e, int max_steps) try {
   CHECK_ARG(e && max_steps >= 1, "bad arguments");
   CU(cudaSetDevice(e->device));
   while ((int)e->prof_ev.size() < max_steps * 4) {
@@ -1842,9 +1855,9 @@ int drs_profile_begin(drs_engine* e, int max_steps) {
   e->prof_n = 0;
   e->prof_on = true;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms, float* post_ms) {
+int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms, float* post_ms) try {
   CHECK_ARG(e && n_steps && pre_ms && gather_ms && post_ms, "NULL argument");
   CU(cudaSetDevice(e->device));
   e->prof_on = false;
@@ -1859,9 +1872,9 @@ int drs_profile_end(drs_engine* e, int* n_steps, float* pre_ms, float* gather_ms
   *n_steps = e->prof_n;
   *pre_ms = (float)a; *gather_ms = (float)b; *post_ms = (float)c;
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_set_option(drs_engine* e, const char* key, int64_t value) {
+int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   CHECK_ARG(e && key, "NULL argument");
   const std::string k(key);
   if (k == "mlp_chain") e->mlp_chain = value != 0;
@@ -1869,9 +1882,9 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) {
   else if (k == "tap_hidden") e->tap_hidden = value != 0;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", key);
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_shard_export(drs_engine* e, void* blob_out) {
+int drs_shard_export(drs_engine* e, void* blob_out) try {
   CHECK_ARG(e && blob_out, "NULL argument");
   CU(cudaSetDevice(e->device));
   ShardBlob b{};
@@ -1885,9 +1898,9 @@ int drs_shard_export(drs_engine* e, void* blob_out) {
   std::memset(blob_out, 0, DRS_SHARD_BLOB_BYTES);
   std::memcpy(blob_out, &b, sizeof(b));
   return DRS_OK;
-}
+} DRS_CATCH
 
-int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs) {
+int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs) try {
   CHECK_ARG(e && all_blobs, "NULL argument");
   CHECK_ARG(world >= 1 && world <= kMaxShardRanks && rank >= 0 && rank < world,
             "rank %d / world %d out of range (max %d ranks)", rank, world, kMaxShardRanks);
@@ -1939,6 +1952,6 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
                 &e->SB, &e->idx_cap, &e->sls_smem, e->table_major, &e->short_seg);
   }
   return rewrite_all_descs(e);
-}
+} DRS_CATCH
 
 }  // extern "C"

@@ -16,6 +16,10 @@ DeepRecSys.py:122-123 computes it.
     python -m deeprecsys_b200.serve --config_file deeprecsys_b200/models/configs/dlrm_rm1.json \
         --num_batches 32 --max_mini_batch_size 1024 --batch_size_distribution normal \
         --avg_mini_batch_size 256 --var_mini_batch_size 32 --avg_arrival_rate 0.25 --nepochs 40
+
+``--serve_rates_ms a,b,c`` sweeps mean inter-arrival times, ``--serve_queries N`` sets the
+queries per rate, ``--serve_ring`` makes every request carry its own tensors through a
+shared-memory ring (utils/input_ring.py) instead of naming a pre-generated batch.
 """
 from __future__ import absolute_import, division, print_function
 
@@ -56,23 +60,39 @@ def _sleep_until(t):
             time.sleep(0)               # yield the core between polls
 
 
-def _generate_load(args, accel_q, report_q, n_total, warmup_queries, arrival_ms, seed):
+def _generate_load(args, accel_q, report_q, n_total, warmup_queries, arrival_ms, seed,
+                   ring=None, dataset=None):
     """Load-generator process (the reference runs loadGenerator() as its own process too,
-    DeepRecSys.py:74-81): Poisson arrivals of ServiceRequests into the bounded accel queue."""
+    DeepRecSys.py:74-81): Poisson arrivals of ServiceRequests into the bounded accel queue.
+    With ``ring``: every request carries its inputs — the generator writes rows [0, B) of batch
+    ``batch_id`` of its own copy of the dataset into the next ring slot and sends a
+    TensorServiceRequest naming the slot (the engine then reads nothing from its own dataset)."""
     from deeprecsys_b200.accelInferenceEngine import _direct_put
+    from deeprecsys_b200.utils.packets import TensorServiceRequest
     sys.setswitchinterval(1e-4)
     put = _direct_put(accel_q)          # same bytes as Queue.put, written without a feeder thread
     rng = np.random.RandomState(seed)
     sizes = query_sizes(args, n_total, rng)
     gaps = rng.exponential(arrival_ms / 1000.0, n_total)
     nb = max(1, args.num_batches)
+    ring_desc = ring.descriptor() if ring is not None else None
     t_next = time.time()
     t_first = None
     for i in range(n_total):
         t_next += gaps[i]
         _sleep_until(t_next)
-        req = ServiceRequest(batch_id=i % nb, epoch=i // nb, batch_size=int(sizes[i]), sub_id=0,
-                             total_sub_batches=1, exp_packet=(i < warmup_queries))
+        if ring is None:
+            req = ServiceRequest(batch_id=i % nb, epoch=i // nb, batch_size=int(sizes[i]),
+                                 sub_id=0, total_sub_batches=1, exp_packet=(i < warmup_queries))
+        else:
+            # the query "arrives" with its tensors: writing them into the slot is the client's
+            # work and happens before the arrival stamp
+            lX, lS_l, lS_i = dataset
+            b, B, slot = i % nb, int(sizes[i]), i % ring.n_slots
+            counts = ring.write(slot, lX[b] if ring.m_den > 0 else None, lS_i[b], lS_l[b], B)
+            req = TensorServiceRequest(ring=ring_desc, slot=slot, counts=counts, batch_id=b,
+                                       epoch=i // nb, batch_size=B, sub_id=0,
+                                       total_sub_batches=1, exp_packet=(i < warmup_queries))
         req.arrival_time = time.time()
         if i == warmup_queries:
             t_first = req.arrival_time
@@ -87,8 +107,22 @@ class SystemHarness(object):
     DeepRecSys.py: the load generator is its own process, this (parent) process only collects
     responses (DeepRecSys.py:92-123)."""
 
-    def __init__(self, args):
+    def __init__(self, args, ring=False):
         self.args = args
+        self.ring, self.dataset = None, None
+        if ring:
+            # the load generator's own copy of the queries (same seed -> the data every engine
+            # process regenerates) and the shared-memory ring their tensors travel through
+            from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
+            from deeprecsys_b200.spec import ModelSpec
+            from deeprecsys_b200.utils.input_ring import SharedInputRing, slots_needed
+            np.random.seed(args.numpy_rand_seed)
+            _, lX, lS_l, lS_i = DLRMDataGenerator(args).generate_input_data()
+            self.dataset = (lX, lS_l, lS_i)
+            spec = ModelSpec(args)
+            mb = int(args.max_mini_batch_size)
+            self.ring = SharedInputRing.create(slots_needed(32, 4), spec.T, spec.m_den, mb,
+                                               mb * max(1, spec.L))
         self.ctx = ctx = mp.get_context("fork")   # DeepRecSys.py uses the default (fork) start method
         self.accel_q = ctx.Queue(maxsize=32)                  # DeepRecSys.py:45
         self.resp_q, self.ready_q = ctx.Queue(), ctx.Queue()
@@ -104,7 +138,7 @@ class SystemHarness(object):
         report_q = self.ctx.Queue()
         gen = self.ctx.Process(target=_generate_load,
                                args=(self.args, self.accel_q, report_q, n_total, warmup_queries,
-                                     arrival_ms, seed))
+                                     arrival_ms, seed, self.ring, self.dataset))
         gen.daemon = True
         gen.start()
         got = []
@@ -157,6 +191,8 @@ class SystemHarness(object):
         self.proc.join(timeout=60)
         if self.proc.is_alive():
             self.proc.terminate()
+        if self.ring is not None:
+            self.ring.close()
 
 
 def run_system(args, n_queries, arrival_ms, seed=0, warmup_queries=20):
@@ -168,18 +204,20 @@ def run_system(args, n_queries, arrival_ms, seed=0, warmup_queries=20):
         h.close()
 
 
-def sweep(args, rates_ms, n_queries, target_p99_ms=None):
+def sweep(args, rates_ms, n_queries, target_p99_ms=None, ring=False):
     """Run the experiment at each mean inter-arrival time against ONE engine process; report
-    the best throughput whose p99 meets ``target_p99_ms`` (args.target_latency by default)."""
+    the best throughput whose p99 meets ``target_p99_ms`` (args.target_latency by default).
+    ``ring``: requests carry their inputs through a shared-memory ring (TensorServiceRequest)."""
     target = float(target_p99_ms if target_p99_ms is not None else args.target_latency)
-    h = SystemHarness(args)
+    h = SystemHarness(args, ring=ring)
     try:
         rows = [h.run(n_queries, r, seed=17 + i) for i, r in enumerate(rates_ms)]
     finally:
         h.close()
     ok = [r for r in rows if r["p99_ms"] <= target and r["failed"] == 0]
     best = max(ok, key=lambda r: r["inferences_per_s"]) if ok else None
-    return {"target_p99_ms": target, "runs": rows, "best": best}
+    return {"target_p99_ms": target, "runs": rows, "best": best,
+            "inputs": "shared-memory ring (TensorServiceRequest)" if ring else "batch_id"}
 
 
 def main(argv=None):
@@ -193,11 +231,14 @@ def main(argv=None):
         i = argv.index("--serve_queries")
         n_queries = int(argv[i + 1])
         del argv[i:i + 2]
+    ring = "--serve_ring" in argv
+    if ring:
+        argv.remove("--serve_ring")
     args = cli(argv)
     if not args.model_name:
         args.model_name = {"dlrm": "rm1"}.get(args.model_type, args.model_type)
     rates = rates or [args.avg_arrival_rate]
-    out = sweep(args, rates, n_queries)
+    out = sweep(args, rates, n_queries, ring=ring)
     print(json.dumps(out))
     return 0
 

@@ -120,6 +120,16 @@ class SharedInputRing(object):
         if self.m_den > 0:
             self.dense(slot)[:B] = np.asarray(dense, dtype=np.float32)[:B]
         L, I = self.lengths(slot), self.ids(slot)
+        if (isinstance(ids, np.ndarray) and isinstance(lengths, np.ndarray) and ids.ndim == 2
+                and lengths.ndim == 2):
+            # [T, n] arrays (the generator's layout): one 2-D copy when every table has the
+            # same number of lookups
+            counts = lengths[:, :B].sum(axis=1)
+            n = int(counts[0]) if self.T > 0 else 0
+            if (counts == n).all() and n <= self.max_lookups and ids.shape[1] >= n:
+                L[:, :B] = lengths[:, :B]
+                I[:, :n] = ids[:, :n]
+                return [n] * self.T
         counts = []
         for t in range(self.T):
             lt = np.asarray(lengths[t])[:B]

@@ -37,7 +37,9 @@ enum {
   DRS_ERR_CUDA = 2,        /* CUDA runtime failure, message has the cudaError string */
   DRS_ERR_STATE = 3,       /* weights/tables/batch not loaded yet */
   DRS_ERR_INDEX = 4,       /* SparseLengthsSum enforce: idx out of range or sum(len) != len(idx) */
-  DRS_ERR_COMM = 5         /* peer-memory / multi-GPU exchange setup failure */
+  DRS_ERR_COMM = 5,        /* peer-memory / multi-GPU exchange setup failure */
+  DRS_ERR_HOST = 6         /* host-side failure inside the library (out of memory, any C++
+                              exception): caught at the boundary, never thrown through it */
 };
 
 /* model graphs (reference: models/dlrm_s_caffe2.py, wide_and_deep.py, ncf.py, din.py,

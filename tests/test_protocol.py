@@ -210,19 +210,21 @@ from deeprecsys_b200.utils.utils import cli
 from oracle.cpu_inference_engine import OracleBackend
 accel_mod.BACKEND_FACTORY = OracleBackend          # CPU test tier only: no GPU here
 args = cli(%r)
-print(json.dumps(serve.sweep(args, [2.0, 1.0], 60, target_p99_ms=1000.0)))
+print(json.dumps(serve.sweep(args, [2.0, 1.0], 60, target_p99_ms=1000.0, ring=%r)))
 """
 
 
-def test_serving_harness_reports_latency_percentiles():
+@pytest.mark.parametrize("ring", [False, True], ids=["batch_id", "ring"])
+def test_serving_harness_reports_latency_percentiles(ring):
     """deeprecsys_b200.serve drives the engine through the same Queue protocol with Poisson
-    arrivals; here against the oracle-backed fake (no GPU in this tier).  Run in a fresh
+    arrivals; here against the oracle-backed fake (no GPU in this tier).  ``ring``: every
+    request carries its tensors through the shared-memory ring.  Run in a fresh
     interpreter: the harness forks the engine process, and a child forked from this
     (multi-threaded, torch-using) pytest process can deadlock in torch's thread pool."""
     import json
     argv = SMALL_SYSTEM + ["--batch_size_distribution", "normal", "--avg_mini_batch_size", "20",
                            "--var_mini_batch_size", "6", "--model_accel", "--queue"]
-    proc = subprocess.run([sys.executable, "-c", HARNESS_SCRIPT % (argv,)], cwd=ROOT,
+    proc = subprocess.run([sys.executable, "-c", HARNESS_SCRIPT % (argv, ring)], cwd=ROOT,
                           env=dict(os.environ, PYTHONPATH=ROOT, PYTHONWARNINGS="ignore"),
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert proc.returncode == 0, proc.stdout[-3000:]
@@ -233,6 +235,8 @@ def test_serving_harness_reports_latency_percentiles():
         assert r["p50_ms"] <= r["p95_ms"] <= r["p99_ms"] <= r["max_ms"]
         assert 1 <= r["mean_query_size"] <= 64 and r["inferences_per_s"] > 0
     assert res["best"] is not None
+    assert res["inputs"].startswith("shared-memory ring" if ring else "batch_id")
+    assert not glob.glob("/dev/shm/drs_ring_*")          # the ring file is removed on close
 
 
 # ------------------------------------------------------------------ tier 2
