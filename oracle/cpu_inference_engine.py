@@ -15,7 +15,6 @@ Two stand-ins used by the protocol tests (tests/test_protocol.py), which run the
 from __future__ import absolute_import, division, print_function
 
 import os
-import sys
 import time
 
 import numpy as np

@@ -5,7 +5,6 @@ profiler against golden fixtures recorded from the reference's own functions
 wired into DLRMDataGenerator's ``--data_generation synthetic`` mode."""
 import os
 import random
-import sys
 
 import numpy as np
 import pytest
