@@ -20,7 +20,7 @@ the stream is a sequence of "rows" of L doubles; sample k of a table receives
 the k-th row whose L rounded ids are all distinct.  Drawing exactly as many
 rows as are still missing, filtering, and repeating consumes precisely the
 same doubles as the reference's redraw loop (the last block drawn contains only
-accepted rows, so nothing is over-drawn).  tests/test_datagen.py checks this
+accepted rows, so nothing is over-drawn).  tests/test_spec_surface.py checks this
 against the reference generator itself and against tests/golden fixtures.
 
 Layout returned (numpy instead of python lists, same values):
