@@ -91,13 +91,3 @@ def test_rng_is_consumed_like_an_engine_process_before_the_parameters():
 def test_no_cpu_mode():
     with pytest.raises(SystemExit):
         standalone.run(cli(SMALL), engine_factory=FakeEngine, out=lambda *a: None)
-
-
-@pytest.mark.gpu
-def test_standalone_run_on_the_gpu():
-    lines = []
-    res = standalone.run(cli(SMALL + ["--use_accel"]),
-                         out=lambda *a: lines.append(" ".join(str(x) for x in a)))
-    (tup,) = parse_like_the_reference(lines)
-    assert len(tup) == 6 and all(v >= 0 for v in tup)
-    assert res["device_compute_ms"] > 0 and res["iterations"] == 6
