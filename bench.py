@@ -77,6 +77,9 @@ def parse_args():
                         "profile name under deeprecsys_b200/data_generator/profile/ (zipf1.05, "
                         "zipf1.2) or a path (--data_generation synthetic; not the headline "
                         "workload — L2 hits raise the gather above the HBM roofline)")
+    p.add_argument("--locality_sorted", action="store_true",
+                   help="with --locality: sort the ids inside every lookup (as the uniform "
+                        "generator's np.unique does)")
     return p.parse_args()
 
 
@@ -96,6 +99,8 @@ def model_args(opts, batch, num_batches):
     if locality_profile(opts):
         argv += ["--data_generation", "synthetic", "--data_trace_file", locality_profile(opts),
                  "--num_indices_per_lookup_fixed", "True"]
+        if opts.locality_sorted:
+            argv += ["--data_trace_sort_lookups"]
     a = cli(argv)
     if opts.interaction:
         a.arch_interaction_op = opts.interaction
@@ -595,7 +600,9 @@ def run_b200(opts):
                                        % (opts.shard, world) if sharded else "replica x%d" % world),
                        "l2_policy": "inputs larger than L2 (4.1 GB tables, %s; "
                                     "%d staged batches cycled)"
-                                    % ("LRU stack-distance ids, profile %s" % opts.locality
+                                    % ("LRU stack-distance ids%s, profile %s"
+                                       % (" sorted inside each lookup" if opts.locality_sorted
+                                          else "", opts.locality)
                                        if opts.locality else "uniform ids", nb),
                        "mlp_precision": opts.precision, "lanes": opts.lanes,
                        "numa_node": numa_node},

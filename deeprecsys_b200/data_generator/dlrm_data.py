@@ -125,7 +125,9 @@ class DLRMDataGenerator(object):
             carries across samples and batches;
           * lookups keep the fixed length L the engines' request slicing needs
             (inferenceEngine.py:204-206), in trace order; an id may repeat inside a lookup
-            (SparseLengthsSum then adds that row twice).
+            (SparseLengthsSum then adds that row twice).  ``--data_trace_sort_lookups`` sorts
+            the ids inside every lookup, as the random generator's ``np.unique`` does
+            (same multiset of rows per sample, ascending walk through the table).
         """
         import os
         from deeprecsys_b200.data_generator.trace_generator import (LruTraceGenerator,
@@ -155,6 +157,8 @@ class DLRMDataGenerator(object):
             ids = np.empty((T, n * L), dtype=np.int32)
             for t in range(T):
                 ids[t] = traces[t].generate(n * L)
+            if getattr(self.args, "data_trace_sort_lookups", False):
+                ids.reshape(T, n, L).sort(axis=2)
             lS_i.append(ids)
             lS_l.append(np.full((T, n), L, dtype=np.int32))
         return num_batches, lX, lS_l, lS_i

@@ -122,6 +122,8 @@ ACCEL_FLAGS = (
     ("accel_upload_inputs", _T, False),  # H2D per query instead of pre-staged batches
     ("accel_gpus", int, 1),              # GPUs behind the single accel slot (replicas; sibling
                                          # processes share accelRequestQueue / responseQueue)
+    ("data_trace_sort_lookups", _T, False),  # --data_generation synthetic: sort the ids inside
+                                         # every lookup (the random generator's np.unique does)
 )
 
 

@@ -248,3 +248,20 @@ def test_gpu_parity_on_locality_traces(tmp_path, name):
                 pooled = eng.fetch_stage(_lib.STAGE_POOLED)
                 assert np.array_equal(pooled.view(np.uint32), st["pooled"].view(np.uint32))
                 np.testing.assert_allclose(out, st["out"], rtol=1e-4, atol=1e-5)
+
+
+def test_sorted_lookups_keep_every_samples_multiset_of_rows(tmp_path):
+    """--data_trace_sort_lookups: same ids per sample as the unsorted trace, ascending inside
+    each lookup (what np.unique gives the random generator's lookups); RNG use is unchanged."""
+    plain = _synthetic_args(tmp_path)
+    np.random.seed(plain.numpy_rand_seed)
+    _, _, _, a = DLRMDataGenerator(plain).generate_input_data()
+    tail = np.random.random_sample(2)
+    srt = _synthetic_args(tmp_path, extra=["--data_trace_sort_lookups"])
+    np.random.seed(srt.numpy_rand_seed)
+    _, _, _, b = DLRMDataGenerator(srt).generate_input_data()
+    assert np.array_equal(tail, np.random.random_sample(2))
+    for x, y in zip(a, b):
+        assert np.array_equal(np.sort(x.reshape(3, 16, 5), axis=2), y.reshape(3, 16, 5))
+        assert (np.diff(y.reshape(3, 16, 5), axis=2) >= 0).all()
+    assert any(not np.array_equal(x, y) for x, y in zip(a, b))
