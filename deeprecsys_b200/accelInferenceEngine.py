@@ -158,6 +158,9 @@ class AccelBackend(object):
                 raise ValueError("ring %s is laid out for %d tables / %d dense features, the model "
                                  "has %d / %d" % (desc["path"], ring.T, ring.m_den, self.spec.T,
                                                   self.spec.m_den))
+            if ring.max_batch > self.engine.max_batch:
+                raise ValueError("ring %s holds queries of up to %d samples, the engine serves at "
+                                 "most %d" % (desc["path"], ring.max_batch, self.engine.max_batch))
             try:
                 from deeprecsys_b200 import _lib
                 _lib.check(self.engine.lib.drs_host_register(ring.base_address(), ring.nbytes))
@@ -175,14 +178,34 @@ class AccelBackend(object):
         buf, out_ptr = self._next_out()
         if request.ring is not None:
             ring = self._attach_ring(request.ring)
-            ptrs = ring._ptr_cache.get(request.slot)
-            if ptrs is None:
-                d, i, l = ring.pointers(request.slot)
-                ptrs = (ctypes.c_void_p(d) if d is not None else None,
-                        (ctypes.c_void_p * T)(*i), (ctypes.c_void_p * T)(*l))
-                ring._ptr_cache[request.slot] = ptrs
-            ticket = self.engine.submit_host(ptrs[0], ptrs[1], 0, ptrs[2], B, out_ptr)
-            return ("ticket", ticket, buf, B)
+            slot = int(request.slot)
+            # never trust the descriptor: a slot outside the ring or a query larger than a slot
+            # would make the host loop and the DMA read a neighbouring slot or unmapped memory
+            if not 0 <= slot < ring.n_slots:
+                raise ValueError("request names slot %d of a %d-slot ring" % (slot, ring.n_slots))
+            release = lambda: ring.release(slot)
+            try:
+                if not 0 < B <= ring.max_batch:
+                    raise ValueError("batch_size %d outside the ring's (0, %d]" % (B, ring.max_batch))
+                counts = request.counts
+                if counts is not None and (len(counts) != T or
+                                           max(int(c) for c in counts) > ring.max_lookups):
+                    raise ValueError("request counts %r do not fit a slot of %d lookups x %d tables"
+                                     % (counts, ring.max_lookups, T))
+                if int(ring.lengths(slot)[:, :B].sum(axis=1).max()) > ring.max_lookups:
+                    raise ValueError("slot %d: sum(lengths) exceeds the slot's %d lookups per table"
+                                     % (slot, ring.max_lookups))
+                ptrs = ring._ptr_cache.get(slot)
+                if ptrs is None:
+                    d, i, l = ring.pointers(slot)
+                    ptrs = (ctypes.c_void_p(d) if d is not None else None,
+                            (ctypes.c_void_p * T)(*i), (ctypes.c_void_p * T)(*l))
+                    ring._ptr_cache[slot] = ptrs
+                ticket = self.engine.submit_host(ptrs[0], ptrs[1], 0, ptrs[2], B, out_ptr)
+            except Exception:
+                release()                      # a refused query must not leave its slot busy
+                raise
+            return ("ticket", ticket, buf, B, None, release)
         dense, dptr, ids, is64, lengths = self.engine._prep(request.dense, request.ids,
                                                             request.lengths, B)
         ticket = self.engine.submit_host(
@@ -197,7 +220,11 @@ class AccelBackend(object):
         if handle[0] == "done":
             return handle[1]
         ticket, buf, B = handle[1:4]
-        self.engine.wait(ticket)
+        try:
+            self.engine.wait(ticket)
+        finally:
+            if len(handle) > 5 and handle[5] is not None:
+                handle[5]()                    # ring slot: its H2D copies are done, hand it back
         return buf[:B]
 
     def close(self):
@@ -351,6 +378,31 @@ def _engine_process(args, requestQueue, engine_id, responseQueue, readyQueue, si
             pstats.Stats(prof, stream=f).sort_stats("tottime").print_stats(40)
 
 
+def _wait_for_siblings(siblings, requestQueue, responseQueue, engine_id, args):
+    """Primary of an --accel_gpus slot whose own backend failed while siblings are healthy: serve
+    nothing, let the siblings drain the queue (the sentinel circulates among them), then answer
+    whatever is left with out_batch_size = 0 and forward the final sentinel."""
+    import queue as _queue
+    for p in siblings:
+        p.join()
+    put_response = _direct_put(responseQueue)
+    while True:
+        try:
+            request = requestQueue.get(timeout=1.0)
+        except _queue.Empty:
+            continue
+        if request is None:
+            put_response(None)
+            return
+        now = time.time()
+        put_response(ServiceResponse(consumer_id=engine_id, epoch=request.epoch,
+                                     batch_id=request.batch_id, batch_size=request.batch_size,
+                                     arrival_time=request.arrival_time, process_start_time=now,
+                                     queue_end_time=now, inference_end_time=now, out_batch_size=0,
+                                     total_sub_batches=request.total_sub_batches,
+                                     exp_packet=request.exp_packet, sub_id=request.sub_id))
+
+
 def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):
     np.random.seed(args.numpy_rand_seed)
     np.set_printoptions(precision=args.print_precision)
@@ -371,9 +423,23 @@ def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibli
         print("[Accel] " + failure)
         sys.stdout.flush()
 
-    for _ in siblings:                     # one ready token for the whole accel slot
-        sibling_ready.get()
-    readyQueue.put(True)
+    if sibling:
+        # A replica that could not be built must not touch the shared accelRequestQueue: it would
+        # answer every packet instantly with out_batch_size = 0 and, doing no work, drain the
+        # queue faster than the healthy replicas.  It reports its state and leaves; "never die
+        # silently" (answer with 0, forward the sentinel) is the primary's job alone.
+        readyQueue.put(backend is not None)
+        if backend is None:
+            return
+    else:
+        healthy = sum(1 for _ in siblings if sibling_ready.get())
+        if backend is None and healthy > 0:
+            print("[Accel] primary replica unavailable; %d sibling replica(s) serve the queue"
+                  % healthy)
+            sys.stdout.flush()
+            readyQueue.put(True)           # one ready token for the whole accel slot
+            return _wait_for_siblings(siblings, requestQueue, responseQueue, engine_id, args)
+        readyQueue.put(True)
 
     # multiprocessing.Queue.put hands the response to a feeder thread; while this loop is busy
     # (requests always pending) that thread only gets the GIL at a switch interval, 5 ms by

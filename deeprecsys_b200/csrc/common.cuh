@@ -5,9 +5,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace drs {
 
 constexpr int kWarp = 32;
+
+// Function attributes (opt-in dynamic shared memory) are per device.  `mask` is one static per
+// call site: returns true the first time the site is reached on the CURRENT device (bit =
+// device ordinal), so a second engine on another GPU of the same process gets its own opt-in.
+inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  const uint64_t bit = uint64_t(1) << dev;
+  return (mask.fetch_or(bit) & bit) == 0;
+}
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

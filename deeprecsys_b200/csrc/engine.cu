@@ -461,12 +461,10 @@ int run_mlp(drs_engine* e, Lane& ln, Mlp& m, std::vector<float*>& ys, const floa
 
 template <int LPR, bool DOT>
 int launch_gather_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid, size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  if (first_use_on_device(attr_set))
     CU(cudaFuncSetAttribute(k_sls_gather<LPR, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             160 * 1024));
-    attr_set = true;
-  }
   k_sls_gather<LPR, DOT><<<grid, kSlsThreads, smem, st>>>(p);
   CU(cudaGetLastError());
   e->launches += 1;
@@ -476,12 +474,10 @@ int launch_gather_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid
 template <int LPR, bool SHORT>
 int launch_gather_persist_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid,
                             size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};
+  if (first_use_on_device(attr_set))
     CU(cudaFuncSetAttribute(k_sls_gather_persist<LPR, SHORT>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
   k_sls_gather_persist<LPR, SHORT><<<grid, kSlsThreads, smem, st>>>(p);
   CU(cudaGetLastError());
   e->launches += 1;
@@ -1226,13 +1222,12 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) try {
         }
       }
       {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<uint64_t> attr_set{0};
+        if (first_use_on_device(attr_set)) {
           CUB(cudaFuncSetAttribute(k_rnn_tanh, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)rnn_smem_bytes(kRnnMaxH)));
           CUB(cudaFuncSetAttribute(k_rnn_tanh4, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)rnn4_smem_bytes(kRnnMaxH)));
-          attr_set = true;
         }
       }
       break;

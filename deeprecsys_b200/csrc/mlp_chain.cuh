@@ -365,12 +365,11 @@ inline int chain_launch(const float* X, int64_t ldx, int64_t x_rows, const Chain
       p.bias[l] = h.bias; p.tap[l] = (l < n - 1) ? h.tap : nullptr; p.ld_tap[l] = h.ld_tap;
     }
   }
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};
+  if (first_use_on_device(attr)) {
     cudaError_t e = cudaFuncSetAttribute(k_mlp_chain, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kChainSmem);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   k_mlp_chain<<<ceil_div(M, kTcBM), kTcThreads, kChainSmem, stream>>>(mx, mw[0], mw[1], mw[2],
                                                                      mw[3], p);

@@ -408,12 +408,11 @@ inline bool tc_fc_supported(int N, int K, int64_t ldx, const float* X) {
 template <int BN>
 inline cudaError_t tc_launch_bn(const CUtensorMap& mx, const CUtensorMap& mw, const TcFcParams& p,
                                 dim3 grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<uint64_t> attr{0};
+  if (first_use_on_device(attr)) {
     cudaError_t e = cudaFuncSetAttribute(k_fc_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tc_smem_bytes(BN));
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   k_fc_tc<BN><<<grid, kTcThreads, tc_smem_bytes(BN), stream>>>(mx, mw, p);
   return cudaGetLastError();

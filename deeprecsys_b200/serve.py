@@ -89,6 +89,7 @@ def _generate_load(args, accel_q, report_q, n_total, warmup_queries, arrival_ms,
             # work and happens before the arrival stamp
             lX, lS_l, lS_i = dataset
             b, B, slot = i % nb, int(sizes[i]), i % ring.n_slots
+            ring.acquire(slot)              # released by the engine when the slot's query is done
             counts = ring.write(slot, lX[b] if ring.m_den > 0 else None, lS_i[b], lS_l[b], B)
             req = TensorServiceRequest(ring=ring_desc, slot=slot, counts=counts, batch_id=b,
                                        epoch=i // nb, batch_size=B, sub_id=0,
@@ -121,8 +122,10 @@ class SystemHarness(object):
             self.dataset = (lX, lS_l, lS_i)
             spec = ModelSpec(args)
             mb = int(args.max_mini_batch_size)
-            self.ring = SharedInputRing.create(slots_needed(32, 4), spec.T, spec.m_den, mb,
-                                               mb * max(1, spec.L))
+            consumers = int(getattr(args, "accel_gpus", 1) or 1)
+            depth = max(4, int(getattr(args, "accel_coalesce", 0) or 0) * 2)
+            self.ring = SharedInputRing.create(slots_needed(32, depth, consumers), spec.T,
+                                               spec.m_den, mb, mb * max(1, spec.L))
         self.ctx = ctx = mp.get_context("fork")   # DeepRecSys.py uses the default (fork) start method
         self.accel_q = ctx.Queue(maxsize=32)                  # DeepRecSys.py:45
         self.resp_q, self.ready_q = ctx.Queue(), ctx.Queue()

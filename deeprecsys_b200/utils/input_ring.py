@@ -12,13 +12,15 @@ query); the accel engine maps the same file once, page-locks it (``drs_host_regi
 hands slot pointers straight to ``drs_submit_host`` — the H2D copies read the producer's bytes,
 there is no host-side copy in the engine.
 
-Slot reuse: the producer writes slot ``i % n_slots`` for its i-th request and then ``put``s the
-request on the bounded accel queue.  At that moment at most ``queue maxsize`` requests wait in
-the queue, ``depth`` are in flight in the engine and one is being handed over, so slot ``i`` was
-last used by a request whose response has already been sent when
-``n_slots >= maxsize + depth + 2`` (``slots_needed``).
+Slot reuse is explicit: the mapping starts with one ``busy`` byte per slot.  The producer
+``acquire``s a slot (waits while it is busy, then marks it), writes the tensors and ``put``s the
+request; the engine ``release``s the slot once the query that reads it has completed (its H2D
+copies are done by then).  Nothing depends on how many requests the queue, the engine lanes,
+a coalescing window or several ``--accel_gpus`` consumers may hold at once; ``slots_needed`` is
+only a sizing hint that keeps the producer from ever having to wait.
 
-Layout of one slot (all offsets 64-byte aligned), ids of table t at ``t * max_lookups``:
+Layout: ``busy uint8 [n_slots]`` (padded to 64 bytes), then the slots.  One slot (all offsets
+64-byte aligned), ids of table t at ``t * max_lookups``:
     dense   float32 [max_batch, m_den]
     lengths int32   [T, max_batch]
     ids     int32   [T, max_lookups]
@@ -37,8 +39,10 @@ def _up(n):
     return (int(n) + _ALIGN - 1) // _ALIGN * _ALIGN
 
 
-def slots_needed(queue_maxsize, depth):
-    return int(queue_maxsize) + int(depth) + 2
+def slots_needed(queue_maxsize, depth, consumers=1):
+    """Slots so that the producer never waits: what the bounded queue holds + what every consumer
+    process may hold in flight (``depth`` each, + 1 being handed over) + 1 being written."""
+    return int(queue_maxsize) + int(consumers) * (int(depth) + 1) + 1
 
 
 class SharedInputRing(object):
@@ -53,7 +57,8 @@ class SharedInputRing(object):
         self.off_lengths = _up(self.max_batch * self.m_den * 4)
         self.off_ids = self.off_lengths + _up(self.T * self.max_batch * 4)
         self.slot_bytes = self.off_ids + _up(self.T * self.max_lookups * 4)
-        self.nbytes = self.slot_bytes * self.n_slots
+        self.header_bytes = _up(self.n_slots)          # busy flags, one byte per slot
+        self.nbytes = self.header_bytes + self.slot_bytes * self.n_slots
         flags = os.O_RDWR | (os.O_CREAT | os.O_EXCL if owner else 0)
         fd = os.open(path, flags, 0o600)
         try:
@@ -66,6 +71,9 @@ class SharedInputRing(object):
         finally:
             os.close(fd)
         self._bytes = np.frombuffer(self._map, dtype=np.uint8)
+        self._busy = self._bytes[:self.n_slots]
+        if owner:
+            self._busy[:] = 0
         self.registered = False
 
     # ------------------------------------------------------------------ construction
@@ -90,11 +98,15 @@ class SharedInputRing(object):
     def base_address(self):
         return self._bytes.ctypes.data
 
-    def _view(self, slot, off, dtype, shape):
+    def _check_slot(self, slot):
         slot = int(slot)
         if not 0 <= slot < self.n_slots:
             raise IndexError("slot %d outside [0, %d)" % (slot, self.n_slots))
-        start = slot * self.slot_bytes + off
+        return slot
+
+    def _view(self, slot, off, dtype, shape):
+        slot = self._check_slot(slot)
+        start = self.header_bytes + slot * self.slot_bytes + off
         count = int(np.prod(shape))
         return self._bytes[start:start + count * 4].view(dtype).reshape(shape)
 
@@ -106,6 +118,27 @@ class SharedInputRing(object):
 
     def ids(self, slot):
         return self._view(slot, self.off_ids, np.int32, (self.T, self.max_lookups))
+
+    # ------------------------------------------------------------------ slot ownership
+    def acquire(self, slot, timeout_s=30.0):
+        """Producer: wait until the engine has released ``slot`` (its previous query completed),
+        then mark it busy.  Raises TimeoutError when the slot never comes back."""
+        import time
+        slot = self._check_slot(slot)
+        if self._busy[slot]:
+            deadline = time.time() + timeout_s
+            while self._busy[slot]:
+                if time.time() > deadline:
+                    raise TimeoutError("ring slot %d was never released" % slot)
+                time.sleep(0)
+        self._busy[slot] = 1
+
+    def release(self, slot):
+        """Consumer: the query that read ``slot`` is complete; the producer may overwrite it."""
+        self._busy[self._check_slot(slot)] = 0
+
+    def is_busy(self, slot):
+        return bool(self._busy[self._check_slot(slot)])
 
     # ------------------------------------------------------------------ producer
     def write(self, slot, dense, ids, lengths, batch_size):
@@ -158,14 +191,14 @@ class SharedInputRing(object):
 
     def pointers(self, slot):
         """(dense address | None, [ids address per table], [lengths address per table])."""
-        base = self.base_address() + int(slot) * self.slot_bytes
+        base = self.base_address() + self.header_bytes + self._check_slot(slot) * self.slot_bytes
         return (base + self.off_dense if self.m_den > 0 else None,
                 [base + self.off_ids + t * self.max_lookups * 4 for t in range(self.T)],
                 [base + self.off_lengths + t * self.max_batch * 4 for t in range(self.T)])
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
-        self._bytes = None
+        self._bytes = self._busy = None
         try:
             self._map.close()
         except (BufferError, ValueError):

@@ -63,6 +63,8 @@ class OracleBackend(object):
         dense = np.array(dense[:B]) if self.spec.m_den > 0 else None
         ids = [torch.as_tensor(np.array(i), dtype=torch.int64) for i in ids]
         lengths = [np.array(l[:B], dtype=np.int32) for l in lengths]
+        if request.ring is not None:
+            ring.release(request.slot)          # copied out: the producer may reuse the slot
         return self.model.forward(dense, ids, lengths).numpy()
 
     def close(self):

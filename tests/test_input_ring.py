@@ -71,6 +71,31 @@ def test_ring_layout_write_read_and_pointers():
     assert not os.path.exists(path)
 
 
+def test_ring_slots_are_handed_back_explicitly():
+    """Slot reuse does not rely on counting what the queue and the engine may hold: a slot is
+    busy from ``acquire`` until the consumer ``release``s it, in whichever process."""
+    ring = SharedInputRing.create(n_slots=2, n_tables=4, m_den=13, max_batch=16, max_lookups=160)
+    try:
+        assert ring.base_address() % 64 == 0 and ring.header_bytes % 64 == 0
+        ring.acquire(0)
+        assert ring.is_busy(0) and not ring.is_busy(1)
+        with pytest.raises(TimeoutError):
+            ring.acquire(0, timeout_s=0.05)                  # still owned by the consumer
+        other = SharedInputRing.attach(ring.descriptor())    # the flags live in the mapping
+        assert other.is_busy(0)
+        other.release(0)
+        other.close()
+        ring.acquire(0, timeout_s=0.05)
+        for bad in (-1, 2):
+            with pytest.raises(IndexError):
+                ring.pointers(bad)
+            with pytest.raises(IndexError):
+                ring.release(bad)
+        assert slots_needed(32, 3) == 37 and slots_needed(32, 3, consumers=8) == 65
+    finally:
+        ring.close()
+
+
 def test_ring_is_shared_between_processes():
     ring = SharedInputRing.create(n_slots=2, n_tables=4, m_den=13, max_batch=16, max_lookups=160)
     try:

@@ -148,6 +148,29 @@ def test_accel_gpus_siblings_share_the_accel_slot(tmp_path, monkeypatch):
     assert sorted(int(f.split("_")[1]) for f in served) == [0, 1, 2]    # on devices 0, 1, 2
 
 
+class BadDeviceBackend(PidBackend):
+    """Replica on device DRS_TEST_BAD_DEVICE cannot be built (missing GPU / OOM / bad spec)."""
+    def __init__(self, args):
+        if int(args.accel_device) == int(os.environ["DRS_TEST_BAD_DEVICE"]):
+            raise RuntimeError("device %d unavailable" % int(args.accel_device))
+        PidBackend.__init__(self, args)
+
+
+@pytest.mark.parametrize("bad_device", [1, 0])
+def test_a_failed_replica_never_consumes_requests(tmp_path, monkeypatch, bad_device):
+    """--accel_gpus 3 with one replica that fails to initialise (a sibling, or the primary):
+    the broken process must not answer packets with out_batch_size = 0 while healthy replicas
+    exist — every request is served by a healthy replica, one ready token, one sentinel."""
+    monkeypatch.setenv("DRS_TEST_PID_DIR", str(tmp_path))
+    monkeypatch.setenv("DRS_TEST_BAD_DEVICE", str(bad_device))
+    reqs = [_req(i % 3, 4 + i % 5, epoch=i // 3) for i in range(60)]
+    out = _run_engine(BadDeviceBackend, reqs, extra=["--accel_gpus", "3", "--accel_device", "0"])
+    assert len(out) == 60
+    assert all(r.out_batch_size == r.batch_size for r in out)          # nobody answered with 0
+    served = os.listdir(str(tmp_path))
+    assert sorted({int(f.split("_")[1]) for f in served}) == sorted({0, 1, 2} - {bad_device})
+
+
 class PipelinedBackend(FakeBackend):
     """submit/complete backend with 3 packets in flight, like the real engine's lanes."""
     depth = 3
@@ -234,7 +257,13 @@ def test_serving_harness_reports_latency_percentiles(ring):
         assert r["queries"] == 60 and r["failed"] == 0
         assert r["p50_ms"] <= r["p95_ms"] <= r["p99_ms"] <= r["max_ms"]
         assert 1 <= r["mean_query_size"] <= 64 and r["inferences_per_s"] > 0
-    assert res["best"] is not None
+    # structure only — this tier has no wall-clock bar (the oracle-backed engine's speed depends
+    # on the host): "best" is the fastest run that met the target, or None when none did
+    ok = [r for r in res["runs"] if r["p99_ms"] <= res["target_p99_ms"] and r["failed"] == 0]
+    if ok:
+        assert res["best"]["inferences_per_s"] == max(r["inferences_per_s"] for r in ok)
+    else:
+        assert res["best"] is None
     assert res["inputs"].startswith("shared-memory ring" if ring else "batch_id")
     assert not glob.glob("/dev/shm/drs_ring_*")          # the ring file is removed on close
 
