@@ -3,20 +3,26 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-One "step" = one pass of the hot path (lengths->offsets already staged, bottom
-MLP, K1 multi-table SparseLengthsSum gather + cat interaction, top MLP) over one
-batch of ``--batch`` synthetic RMC1 samples (default 16384 = 16 coalesced
-1024-item queries; reference shape: models/configs/dlrm_rm1.json,
-data_generator/dlrm_data_caffe2.py).  Tables (4.1 GB) are far larger than the
-126 MB L2 and every step reads a different staged batch, so no L2 flush is
-needed between timed iterations ("inputs larger than L2").
+One "step" = one pass of the hot path (bottom MLP, K1 multi-table SparseLengthsSum gather + cat
+interaction, top MLP) over one batch of ``--batch`` synthetic RMC1 samples (default 16384 = 16
+coalesced 1024-item queries; reference shape: models/configs/dlrm_rm1.json,
+data_generator/dlrm_data_caffe2.py).  Tables (4.1 GB) are far larger than the 126 MB L2 and
+every step reads a different staged batch, so no L2 flush is needed between timed iterations
+("inputs larger than L2").
 
-Prints ONE JSON line (see the keys at the bottom).  ``value`` is measured with
-the inputs resident in HBM; ``e2e`` goes through the C-ABI with pinned HOST
-buffers (H2D of ids/lengths/dense and D2H of the scores inside the timed
-region); ``roofline`` is the K1 gather kernel timed with CUDA events on the
-engine's stream inside the timed region; ``cpu_baseline`` is the torch-CPU port
-of the reference's CPU engine timed on this box's host cores.
+Prints ONE JSON line.  Headline keys (BASELINE.json's metric on RMC1, replicas at N > 1):
+  value          device-timed, inputs resident in HBM
+  e2e            same step through the C-ABI with pinned HOST buffers (H2D + D2H inside)
+  roofline       K1 gather kernel, CUDA events on the engine's stream inside the timed region
+  cpu_baseline   torch-CPU port of the reference's CPU engine on this box's host cores
+  system         the metric's "at p99" half: accelInferenceEngine behind multiprocessing Queues
+Beside them, in the same line:
+  secondary      (N = 1) the other BASELINE configs — rm2, rm3, wnd, ncf, din, din254 — each with
+                 value / e2e / cpu_baseline / roofline (HBM GB/s or tensor TFLOP/s) / parity
+  sharded        (N > 1) the split north_star names: RMC1 table-wise, RMC1 row-wise and RMC3
+                 table-wise across the N GPUs, pooled vectors exchanged by K1's peer stores over
+                 NVLink; each leg with value / roofline / clocks and an in-bench parity check of
+                 sampled rows against the CPU oracle (outside the timed region)
 """
 from __future__ import absolute_import, division, print_function
 
@@ -34,13 +40,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CONFIG_DIR = os.path.join(ROOT, "deeprecsys_b200", "models", "configs")
 CONFIGS = {
     "rm1": "dlrm_rm1.json", "rm2": "dlrm_rm2.json", "rm3": "dlrm_rm3.json",
     "wnd": "wide_and_deep.json", "ncf": "ncf.json", "din": "din.json",
     "dien": "dien.json", "mtwnd": "mtwnd.json",
 }
+# DIN exactly as utils/utils.py:132-149 expands it when the same values arrive as FLAGS instead of
+# through din.json (the JSON overrides the expansion): profile + 251 behaviour tables + ad + ctx
+DIN254_ARGV = ["--model_type", "din", "--model_name", "din",
+               "--arch_embedding_size", "1000000-100000-10000000-10000000",
+               "--user_behavior_tables", "250", "--arch_sparse_feature_size", "32",
+               "--arch_mlp_bot", "1", "--arch_mlp_top", "200-80-2", "--arch_interaction_op", "cat",
+               "--num_indices_per_lookup", "3", "--num_indices_per_lookup_fixed", "True"]
+# samples per step of the secondary configs (sized so that one step is 0.1 - 1 ms of GPU work)
+SECONDARY = [("rm2", 4096), ("rm3", 16384), ("wnd", 16384), ("ncf", 16384), ("din", 16384),
+             ("din254", 4096)]
+ROOFLINE_KIND = {"rm1": "hbm", "rm2": "hbm", "rm3": "tensor", "wnd": "tensor", "ncf": "tensor",
+                 "mtwnd": "tensor", "din": "latency", "din254": "hbm", "dien": "latency"}
 METRIC = "DLRM-RMC1 inferences/sec"
 UNIT = "inferences/s"
+DIST_BACKEND = "nccl"          # tests/test_bench_dryrun.py runs the host logic over gloo
+TABLE_ROWS_CAP = None          # same test: shrink the tables so the dry run needs no 4 GB
 
 
 def parse_args():
@@ -49,28 +70,35 @@ def parse_args():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    p.add_argument("--config", type=str, default="rm1", choices=sorted(CONFIGS))
-    p.add_argument("--batch", type=int, default=16384, help="samples per step")
+    p.add_argument("--config", type=str, default="rm1", choices=sorted(CONFIGS) + ["din254"])
+    p.add_argument("--batch", type=int, default=16384, help="samples per step (per GPU)")
     p.add_argument("--staged_batches", type=int, default=4)
     p.add_argument("--precision", type=str, default="tf32x3",
                    help="MLP arithmetic: fp32 (FFMA) | tf32x3 (tcgen05, fp32-class) | tf32")
     p.add_argument("--lanes", type=int, default=3)
     p.add_argument("--shard", type=str, default="replica", choices=["replica", "table", "row"],
-                   help="N>1: replica (every rank all tables, own queries) | table (table-wise "
-                        "sharding, pooled vectors exchanged by K1's peer stores over NVLink) | "
-                        "row (row-wise sharding: every rank a row slice of every table, partial "
-                        "pooled vectors exchanged the same way and added at the owner)")
+                   help="N>1, headline workload: replica (every rank all tables, own queries) | "
+                        "table | row.  The default run measures replicas as the headline and "
+                        "table / row / RMC3-table as the `sharded` legs")
     p.add_argument("--interaction", type=str, default=None, help="override: cat | dot")
     p.add_argument("--cpu_seconds", type=float, default=10.0)
     p.add_argument("--cpu_sample", type=int, default=4096)
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_sweep", action="store_true")
     p.add_argument("--no_e2e", action="store_true")
+    p.add_argument("--no_secondary", action="store_true",
+                   help="N=1: skip the rm2 / rm3 / wnd / ncf / din / din254 block")
+    p.add_argument("--secondary", type=str, default=None,
+                   help="comma list to restrict the secondary block, e.g. rm2,wnd")
+    p.add_argument("--no_sharded", action="store_true",
+                   help="N>1: skip the table-/row-sharded legs")
+    p.add_argument("--sharded", type=str, default="rm1:table,rm1:row,rm3:table",
+                   help="N>1: comma list of config:mode sharded legs")
     p.add_argument("--no_system", action="store_true",
                    help="skip the Poisson-arrival serving run through the Queue API")
-    p.add_argument("--system_rates_ms", type=str, default="0.5,0.125,0.09,0.06,0.045",
+    p.add_argument("--system_rates_ms", type=str, default=None,
                    help="mean inter-arrival times (ms) of the serving run")
-    p.add_argument("--system_queries", type=int, default=2000)
+    p.add_argument("--system_queries", type=int, default=4000)
     p.add_argument("--seed", type=int, default=123)
     p.add_argument("--locality", type=str, default=None,
                    help="ids with temporal reuse instead of uniform-random ones: a stack-distance "
@@ -91,35 +119,45 @@ def locality_profile(opts):
     return shipped if os.path.exists(shipped) else opts.locality
 
 
-def model_args(opts, batch, num_batches):
+def model_args(opts, config, batch, num_batches):
     from deeprecsys_b200.utils.utils import cli
-    cfg = os.path.join(ROOT, "deeprecsys_b200", "models", "configs", CONFIGS[opts.config])
-    argv = ["--config_file", cfg, "--num_batches", str(num_batches),
-            "--max_mini_batch_size", str(batch), "--numpy_rand_seed", str(opts.seed)]
-    if locality_profile(opts):
+    if config == "din254":
+        argv = list(DIN254_ARGV)
+    else:
+        argv = ["--config_file", os.path.join(CONFIG_DIR, CONFIGS[config])]
+    argv += ["--num_batches", str(num_batches), "--max_mini_batch_size", str(batch),
+             "--numpy_rand_seed", str(opts.seed)]
+    if locality_profile(opts) and config == opts.config:
         argv += ["--data_generation", "synthetic", "--data_trace_file", locality_profile(opts),
                  "--num_indices_per_lookup_fixed", "True"]
         if opts.locality_sorted:
             argv += ["--data_trace_sort_lookups"]
     a = cli(argv)
-    if opts.interaction:
+    if opts.interaction and config == opts.config:
         a.arch_interaction_op = opts.interaction
+    if TABLE_ROWS_CAP:
+        a.arch_embedding_size = "-".join(str(min(int(r), TABLE_ROWS_CAP))
+                                         for r in a.arch_embedding_size.split("-"))
     return a
 
 
+def synth_table(spec, seed, t):
+    """Random-init table t of the reference's distribution U(+-sqrt(1/n)), drawn in float32 with
+    a fast per-table generator, so any rank can regenerate any table (bench only; the engine's
+    drop-in path uses the reference's exact legacy-RNG draws, deeprecsys_b200/spec.py)."""
+    rows = spec.table_rows[t]
+    rng = np.random.default_rng([seed, t])
+    W = rng.random((rows, spec.D), dtype=np.float32)
+    bound = np.float32(np.sqrt(1.0 / rows))
+    W *= 2 * bound
+    W -= bound
+    return W
+
+
 def synth_tables(spec, seed, only=None):
-    """Random-init tables of the reference's distribution U(+-sqrt(1/n)), drawn in
-    float32 with a fast generator (bench only; the engine's drop-in path uses the
-    reference's exact legacy-RNG draws, deeprecsys_b200/spec.py)."""
-    for t, rows in enumerate(spec.table_rows):
-        if only is not None and t not in only:
-            continue
-        rng = np.random.default_rng([seed, t])
-        W = rng.random((rows, spec.D), dtype=np.float32)
-        bound = np.float32(np.sqrt(1.0 / rows))
-        W *= 2 * bound
-        W -= bound
-        yield t, W
+    for t in range(spec.T):
+        if only is None or t in only:
+            yield t, synth_table(spec, seed, t)
 
 
 def synth_fcs(spec, seed):
@@ -166,7 +204,8 @@ class ClockSampler(object):
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                    "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -191,33 +230,72 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def load_traffic(opts, spec, B, sharded):
+def load_traffic(config, B, sharded, lanes):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the gather kernel from the
-    committed ``ncu --set full`` capture of this same command (profiles/), or None when the
-    capture does not cover this workload."""
-    path = os.path.join(ROOT, "profiles", "r01f_gather_persist_ncu_full_summary.json")
-    if sharded or opts.config != "rm1" or B != 16384 or not os.path.exists(path):
+    committed ``ncu --set full`` capture of this same command (profiles/), or None when no
+    capture covers this workload."""
+    names = {"rm1": ["r02_gather_rm1_ncu_full_summary.json",
+                     "r01f_gather_persist_ncu_full_summary.json"],
+             "rm2": ["r02_gather_rm2_ncu_full_summary.json"]}.get(config, [])
+    want_B = {"rm1": 16384, "rm2": 4096}.get(config)
+    if sharded or B != want_B:
         return None, None
-    with open(path) as f:
-        cap = json.load(f)
-    vals = [l["traffic_bytes_per_launch"] for l in cap["launches"]]
-    return float(np.mean(vals)), "profiles/r01f_gather_persist_ncu_full_summary.json"
+    for name in names:
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as f:
+                cap = json.load(f)
+            vals = [l["traffic_bytes_per_launch"] for l in cap["launches"]]
+            return float(np.mean(vals)), "profiles/" + name
+    return None, None
 
 
 def load_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source).  The tensor-core MLPs run kind::tf32,
+    whose dense peak is half of bf16's."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            d = json.load(f)
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                "measured (MEASURED_PEAKS.json)")
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md: 6.65 TB/s, ~1.4 PFLOP/s sustained bf16)"
+
+
+def workload_text(config, spec, B, staged=True):
+    return ("%s (%s, %s) %d tables x %s rows x D=%d, L=%d, %d samples/step%s"
+            % (config, spec.model_type, spec.interaction_op, spec.T,
+               spec.table_rows[0] if len(set(spec.table_rows)) == 1
+               else "%d..%d" % (min(spec.table_rows), max(spec.table_rows)),
+               spec.D, spec.L, B, ", staged in HBM" if staged else ""))
+
+
+def headline_config(opts, spec, B, world, sharded):
+    """The `config` object of the JSON line; both arms print the same one (the reference arm
+    describes its bounded per-step sample in cpu_baseline.sample)."""
+    cfg = {"workload": "dlrm_%s (%s) %d tables x %s rows x D=%d, L=%d, %d samples/step "
+                       "(=%d coalesced 1024-item queries), staged in HBM"
+                       % (opts.config, spec.interaction_op, spec.T, spec.table_rows[0], spec.D,
+                          spec.L, B, max(1, B // 1024)),
+           "global_batch": B * world,
+           "parallelism": ("%s-sharded x%d (K1 peer stores over NVLink)" % (opts.shard, world)
+                           if sharded else "replica x%d" % world),
+           "l2_policy": "inputs larger than L2 (4.1 GB tables, %s; %d staged batches cycled)"
+                        % ("LRU stack-distance ids%s, profile %s"
+                           % (" sorted inside each lookup" if opts.locality_sorted else "",
+                              opts.locality) if opts.locality else "uniform ids",
+                           opts.staged_batches),
+           "mlp_precision": opts.precision, "lanes": opts.lanes}
+    return cfg
 
 
 # ----------------------------------------------------------------------------
 def run_reference(opts):
-    """--impl reference: the reference's CPU path (torch-CPU port of
-    inferenceEngine.py's net; Caffe2 itself is not importable here) on the host
-    cores, same workload shape, each step a bounded sample."""
+    """--impl reference: the reference's CPU path (torch-CPU port of inferenceEngine.py's net;
+    Caffe2 itself is not importable here) on the host cores, same workload, each step a bounded
+    sample of it."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     import torch
@@ -227,7 +305,7 @@ def run_reference(opts):
     from deeprecsys_b200.spec import ModelSpec
     from oracle.torch_cpu_engine import TorchCpuModel
     n = int(opts.cpu_sample)
-    a = model_args(opts, n, 1)
+    a = model_args(opts, opts.config, n, 1)
     spec = ModelSpec(a)
     _, lX, lS_l, lS_i = DLRMDataGenerator(a).generate_input_data()
     tables = [W for _, W in synth_tables(spec, opts.seed)]
@@ -243,14 +321,14 @@ def run_reference(opts):
     dt = time.perf_counter() - t0
     value = n * opts.steps / dt
     cores = torch.get_num_threads()
-    sample = "%d steps x %d samples of the %s workload" % (opts.steps, n, opts.config)
+    sample = ("each step = the first %d samples of one %d-sample step of the workload "
+              "(%d steps, %.1f s of CPU work)" % (n, opts.batch, opts.steps, dt))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
         "ms_per_step": 1e3 * dt / opts.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dlrm_%s cat, %d samples/step (bounded CPU sample)"
-                   % (opts.config, n)},
+        "config": headline_config(opts, spec, int(opts.batch), max(1, world), False),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample,
                          "what": "torch-CPU port of inferenceEngine.py net "
@@ -262,236 +340,317 @@ def run_reference(opts):
     return 0
 
 
-def run_b200(opts):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+# ----------------------------------------------------------------------------
+class Env(object):
+    """Process-level context: rank / world / torch.distributed handle / helpers."""
 
-    from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
-    from deeprecsys_b200.engine import AccelEngine, bind_to_device_numa_node, pinned_empty
-    from deeprecsys_b200.spec import ModelSpec
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            if DIST_BACKEND == "nccl":
+                torch.cuda.set_device(self.local)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            else:
+                dist.init_process_group(DIST_BACKEND)
+            self.dist = dist
 
-    from deeprecsys_b200 import shard as shardlib
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
 
-    # one process per GPU: sit on the GPU's NUMA node before any pinned buffer is allocated
-    numa_node = bind_to_device_numa_node(local) if world > 1 else -1
-
-    B, nb = int(opts.batch), int(opts.staged_batches)        # B = samples per GPU per step
-    sharded = (world > 1 and opts.shard in ("table", "row"))
-    row_mode = sharded and opts.shard == "row"
-    GB = B * world if sharded else B                           # samples in one enqueued query
-    a = model_args(opts, GB, nb)
-    spec = ModelSpec(a)
-    eng = AccelEngine(args=a, device=local, max_batch=B, precision=opts.precision,
-                      lanes=opts.lanes, max_lookups_per_table=GB * max(1, spec.L),
-                      shard_mode="row" if row_mode else "table", shard_world=world)
-    if sharded:
-        shardlib.connect(eng, dist)
-    keep_host = (rank == 0 and world == 1 and not opts.no_cpu_baseline)
-    host_tables = []
-    only = set(shardlib.owned_tables(spec.T, rank, world)) if (sharded and not row_mode) else None
-    # replica: every rank has its own table contents and queries; table: one global model
-    tseed = opts.seed if sharded else opts.seed + 1000 * rank
-    for t, W in synth_tables(spec, tseed, only):
-        eng.load_table(t, W)
-        if keep_host:
-            host_tables.append(W)
-    fcs = synth_fcs(spec, opts.seed)
-    for (mlp_id, layer), (W, b) in fcs.items():
-        eng.load_fc(mlp_id, layer, W, b)
-
-    np.random.seed(opts.seed + (0 if sharded else rank))
-    _, lX, lS_l, lS_i = DLRMDataGenerator(a).generate_input_data()
-    for j in range(nb):
-        eng.stage_batch(j, lX[j] if spec.m_den > 0 else None,
-                        [lS_i[j][t] for t in range(spec.T)], [lS_l[j][t] for t in range(spec.T)])
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
+    def max_over_ranks(self, x):
+        if self.dist is None:
             return x
         import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([x], dtype=torch.float64,
+                         device="cuda" if DIST_BACKEND == "nccl" else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- value: inputs resident in HBM, device-timed
-    for i in range(max(3, opts.warmup)):
-        eng.enqueue_staged(i % nb, GB)
-    eng.sync()
-    launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    eng.sync()
-    eng.profile_begin(opts.steps)
-    eng.timer_start()
-    for i in range(opts.steps):
-        eng.enqueue_staged(i % nb, GB)
-    ms_total = eng.timer_stop()
-    eng.sync()
-    n_prof, pre_ms, gather_ms, post_ms = eng.profile_end()
-    launches = eng.launch_count() - launches0
-    # nvidia-smi samples every 100 ms and a short timed region can fall between two samples:
-    # keep the very same step loop running (untimed) until the load has lasted >= 0.6 s
-    # (step count derived from the max-over-ranks time so that every rank runs the same number:
-    # table-sharded steps exchange data and must stay in lockstep)
-    ms_total = max_over_ranks(ms_total)
-    ext_steps = int(max(0.0, 600.0 - ms_total) / max(1e-3, ms_total / opts.steps)) + 1
-    ext_steps = min(ext_steps, 20000)
-    for i in range(ext_steps):
-        eng.enqueue_staged(i % nb, GB)
-        if i % 64 == 63:
+    def all_ok(self, ok):
+        """True iff ``ok`` holds on every rank."""
+        return self.max_over_ranks(0.0 if ok else 1.0) == 0.0
+
+    def gather_objects(self, obj):
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+class Workload(object):
+    """One model config on this rank's GPU: engine, parameters, staged synthetic batches."""
+
+    def __init__(self, env, opts, config, B, nb, shard="replica", lanes=None, keep_host=False):
+        from deeprecsys_b200.data_generator.dlrm_data import DLRMDataGenerator
+        from deeprecsys_b200.engine import AccelEngine
+        from deeprecsys_b200.spec import ModelSpec
+        from deeprecsys_b200 import shard as shardlib
+        self.env, self.opts, self.config = env, opts, config
+        world = env.world
+        self.B, self.nb = int(B), int(nb)                      # B = samples per GPU per step
+        self.sharded = world > 1 and shard in ("table", "row")
+        self.row_mode = self.sharded and shard == "row"
+        self.shard = shard if self.sharded else "replica"
+        self.GB = self.B * world if self.sharded else self.B   # samples in one enqueued query
+        self.lanes = int(lanes if lanes is not None else opts.lanes)
+        self.args = a = model_args(opts, config, self.GB, self.nb)
+        self.spec = spec = ModelSpec(a)
+        if self.sharded and spec.model_type == "dien":
+            raise ValueError("DIEN cannot be sharded by samples")
+        self.eng = AccelEngine(args=a, device=env.local, max_batch=self.B,
+                               precision=opts.precision, lanes=self.lanes,
+                               max_lookups_per_table=self.GB * max(1, spec.L),
+                               shard_mode="row" if self.row_mode else "table", shard_world=world)
+        if self.sharded:
+            shardlib.connect(self.eng, env.dist)
+        self.only = (set(shardlib.owned_tables(spec.T, env.rank, world))
+                     if (self.sharded and not self.row_mode) else None)
+        # replica: every rank has its own table contents and queries; sharded: one global model
+        self.tseed = opts.seed if self.sharded else opts.seed + 1000 * env.rank
+        self.host_tables = {} if keep_host else None
+        for t, W in synth_tables(spec, self.tseed, self.only):
+            self.eng.load_table(t, W)
+            if keep_host:
+                self.host_tables[t] = W
+        self.fcs = synth_fcs(spec, opts.seed)
+        for (mlp_id, layer), (W, b) in self.fcs.items():
+            self.eng.load_fc(mlp_id, layer, W, b)
+        np.random.seed(opts.seed + (0 if self.sharded else env.rank))
+        _, self.lX, self.lS_l, self.lS_i = DLRMDataGenerator(a).generate_input_data()
+        T = spec.T
+        for j in range(self.nb):
+            self.eng.stage_batch(j, self.lX[j] if spec.m_den > 0 else None,
+                                 [self.lS_i[j][t] for t in range(T)],
+                                 [self.lS_l[j][t] for t in range(T)])
+
+    def close(self):
+        self.eng.close()
+
+    # ---------------------------------------------------------------- value (device-timed)
+    def measure_value(self, steps, warmup, clocks=True, min_load_ms=600.0):
+        env, eng, nb, GB = self.env, self.eng, self.nb, self.GB
+        for i in range(max(3, warmup)):
+            eng.enqueue_staged(i % nb, GB)
+        eng.sync()
+        launches0 = eng.launch_count()
+        sampler = ClockSampler(env.local) if clocks else None
+        if sampler:
+            sampler.start()
+        env.barrier()
+        eng.sync()
+        eng.profile_begin(steps)
+        eng.timer_start()
+        for i in range(steps):
+            eng.enqueue_staged(i % nb, GB)
+        ms_total = eng.timer_stop()
+        eng.sync()
+        n_prof, pre_ms, gather_ms, post_ms = eng.profile_end()
+        launches = eng.launch_count() - launches0
+        ms_total = env.max_over_ranks(ms_total)
+        out = {"ms_total": ms_total, "ms_per_step": ms_total / steps, "launches": int(launches),
+               "value": env.world * self.B * steps / (ms_total * 1e-3),
+               "prof": (n_prof, pre_ms, gather_ms, post_ms)}
+        if sampler:
+            # nvidia-smi samples every 100 ms and a short timed region can fall between two
+            # samples: keep the very same step loop running (untimed) until the load has lasted
+            # >= min_load_ms (step count derived from the max-over-ranks time so that every rank
+            # runs the same number: sharded steps exchange data and must stay in lockstep)
+            ext = int(max(0.0, min_load_ms - ms_total) / max(1e-3, ms_total / steps)) + 1
+            ext = min(ext, 20000)
+            for i in range(ext):
+                eng.enqueue_staged(i % nb, GB)
+                if i % 64 == 63:
+                    eng.sync()
             eng.sync()
-    eng.sync()
-    barrier()
-    clocks = sampler.stop()
-    clocks["window"] = ("timed region + %d identical untimed steps (sampler period 100 ms)"
-                        % ext_steps)
-    ms_per_step = ms_total / opts.steps
-    value = world * B * opts.steps / (ms_total * 1e-3)
+            env.barrier()
+            ck = sampler.stop()
+            ck["window"] = ("timed region + %d identical untimed steps (sampler period 100 ms)"
+                            % ext)
+            out["clocks"] = ck
+        return out
 
-    # ---------------- roofline of the dominant kernel (K1 gather), same timed region
-    peak, peak_src = load_peaks()
-    bytes_per_sample = spec.gather_bytes_per_sample(fused=True)
-    gather_ms_avg = gather_ms / max(1, n_prof)
-    # per launch: this rank's tables x the query's samples (table mode: T/world tables x B*world
-    # samples = the same bytes as replica mode's T tables x B samples when T % world == 0)
-    # (row mode: all T tables, ~1/world of every sample's lookups)
-    own_frac = (1.0 / world) if row_mode else (len(only) / float(spec.T)) if sharded else 1.0
-    bytes_per_launch = bytes_per_sample * GB * own_frac
-    traffic, traffic_src = load_traffic(opts, spec, B, sharded)
-    # One gather launch per step.  With >= 3 lanes consecutive gather launches overlap each other
-    # on the chip, so a launch's own event-bracketed duration double-counts the shared time; the
-    # average launch duration over the timed region is then region time / launches (the gather
-    # is resident for the whole region).  With <= 2 lanes a persistent gather fills the register
-    # file and launches never overlap: the event-bracketed duration is used as is.
-    overlapped = opts.lanes >= 3
-    launch_ms = ms_per_step if overlapped else gather_ms_avg
-    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
-    # the same kernel timed alone (one query in flight, sync between steps)
-    eng.profile_begin(8)
-    for i in range(8):
-        eng.enqueue_staged(i % nb, GB)
-        eng.sync()
-    n_solo, solo_pre, solo_ms, solo_post = eng.profile_end()
-    solo_ms_avg = solo_ms / max(1, n_solo)
-    tot = max(1e-9, pre_ms + gather_ms + post_ms)
-    solo_tot = max(1e-9, solo_pre + solo_ms + solo_post)
-    roofline = {
-        "kernel": "k_sls_gather_persist (multi-table SparseLengthsSum + cat layout)",
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0, "traffic": traffic,
-        "traffic_source": traffic_src, "alg_bytes_per_launch": bytes_per_launch,
-        "peak_source": peak_src, "alg_bytes_per_sample": bytes_per_sample,
-        "launch_ms_avg": launch_ms,
-        "launch_ms_definition": ("timed region / gather launches (launches overlap across lanes)"
-                                 if overlapped else "CUDA events around each launch"),
-        "event_bracketed_ms_avg": gather_ms_avg,
-        "kernel_alone": {"ms": solo_ms_avg,
-                         "achieved": bytes_per_launch / (solo_ms_avg * 1e-3) / 1e9
-                         if solo_ms_avg > 0 else None,
-                         "frac": bytes_per_launch / (solo_ms_avg * 1e-3) / 1e9 / peak
-                         if solo_ms_avg > 0 else None,
-                         "note": "same launch with one query in flight (no overlap with the MLP "
-                                 "kernels of other lanes), CUDA events around the launch"},
-        # shares of one step with ONE query in flight (kernels run back to back, like ncu's
-        # serialised launch list in profiles/): comparable with the launch list's shares
-        "step_share": {"pre_gather_mlp": solo_pre / solo_tot, "gather": solo_ms / solo_tot,
-                       "post_gather_mlp": solo_post / solo_tot,
-                       "note": "CUDA-event segments of the step with one query in flight "
-                               "(serialised, comparable with profiles/*launches*.csv)"},
-        "step_share_overlapped": {"pre_gather_mlp": pre_ms / tot, "gather": gather_ms / tot,
-                                  "post_gather_mlp": post_ms / tot,
-                                  "note": "same segments in the timed region: lanes overlap, so "
-                                          "segments of different lanes run concurrently and "
-                                          "each is stretched by the sharing"},
-    }
+    def measure_solo(self, n=8):
+        """The same step with one query in flight (sync between steps): kernels back to back."""
+        eng = self.eng
+        eng.profile_begin(n)
+        for i in range(n):
+            eng.enqueue_staged(i % self.nb, self.GB)
+            eng.sync()
+        return eng.profile_end()
 
-    # ---------------- e2e: C-ABI with pinned HOST buffers, H2D + D2H inside
-    e2e, latency = None, None
-    if not opts.no_e2e and not sharded:
+    # ---------------------------------------------------------------- roofline
+    def roofline(self, val, solo=None):
+        spec, opts, env = self.spec, self.opts, self.env
+        hbm_peak, bf16_peak, peak_src = load_peaks()
+        kind = ROOFLINE_KIND.get(self.config, "hbm")
+        n_prof, pre_ms, gather_ms, post_ms = val["prof"]
+        ms_per_step = val["ms_per_step"]
+        tot = max(1e-9, pre_ms + gather_ms + post_ms)
+        out = {}
+        if kind == "tensor":
+            # FC stack on tcgen05 kind::tf32.  achieved = useful (fp32-class) FLOP/s of the whole
+            # step; tf32x3 issues three MMAs per useful product
+            flops = spec.mlp_flops_per_sample() * self.B            # this rank's rows per step
+            peak = 0.5 * bf16_peak
+            achieved = flops / (ms_per_step * 1e-3) / 1e12
+            passes = 3 if opts.precision == "tf32x3" else 1
+            out = {"kernel": "k_fc_tc / k_mlp_chain (tcgen05 kind::tf32 FC stack)",
+                   "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                   "frac": achieved / peak, "traffic": None,
+                   "mma_tflops": achieved * passes, "mma_frac": achieved * passes / peak,
+                   "alg_flops_per_sample": spec.mlp_flops_per_sample(),
+                   "peak_source": peak_src + ": 0.5 x bf16_tflops_sustained (TF32 dense peak is "
+                                             "half of BF16's)",
+                   "note": "whole-step figure: flops of one step / ms_per_step; mma_* counts the "
+                           "%d tcgen05 passes of %s" % (passes, opts.precision)}
+        else:
+            bytes_per_sample = spec.gather_bytes_per_sample(fused=True)
+            own_frac = ((1.0 / env.world) if self.row_mode
+                        else (len(self.only) / float(spec.T)) if self.sharded else 1.0)
+            bytes_per_launch = bytes_per_sample * self.GB * own_frac
+            gather_ms_avg = gather_ms / max(1, n_prof)
+            # One gather launch per step.  With >= 3 lanes consecutive gather launches overlap each
+            # other on the chip, so a launch's own event-bracketed duration double-counts the
+            # shared time; the average launch duration over the timed region is then region time
+            # / launches (the gather is resident for the whole region).  With <= 2 lanes a
+            # persistent gather fills the register file and launches never overlap.
+            overlapped = self.lanes >= 3
+            launch_ms = ms_per_step if overlapped else gather_ms_avg
+            achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+            traffic, traffic_src = load_traffic(self.config, self.B, self.sharded, self.lanes)
+            out = {"kernel": "k_sls_gather_persist (multi-table SparseLengthsSum + cat layout)",
+                   "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": achieved / hbm_peak, "frac_of_8TBs": achieved / 8000.0,
+                   "traffic": traffic, "traffic_source": traffic_src,
+                   "alg_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                   "alg_bytes_per_sample": bytes_per_sample, "launch_ms_avg": launch_ms,
+                   "launch_ms_definition": ("timed region / gather launches (launches overlap "
+                                            "across lanes)" if overlapped
+                                            else "CUDA events around each launch"),
+                   "event_bracketed_ms_avg": gather_ms_avg}
+            if kind == "latency":
+                out["note"] = ("launch/latency-bound at the shipped sizes (%d B of rows per "
+                               "sample): the HBM figure is reported for completeness"
+                               % (spec.T * spec.L * spec.D * 4))
+            if solo is not None:
+                n_solo, solo_pre, solo_ms, solo_post = solo
+                solo_avg = solo_ms / max(1, n_solo)
+                out["kernel_alone"] = {
+                    "ms": solo_avg,
+                    "achieved": bytes_per_launch / (solo_avg * 1e-3) / 1e9 if solo_avg > 0 else None,
+                    "frac": bytes_per_launch / (solo_avg * 1e-3) / 1e9 / hbm_peak
+                    if solo_avg > 0 else None,
+                    "note": "same launch with one query in flight (no overlap with the MLP "
+                            "kernels of other lanes), CUDA events around the launch"}
+        if solo is not None:
+            n_solo, solo_pre, solo_ms, solo_post = solo
+            solo_tot = max(1e-9, solo_pre + solo_ms + solo_post)
+            # shares of one step with ONE query in flight (kernels run back to back, like ncu's
+            # serialised launch list in profiles/): comparable with the launch list's shares
+            out["step_share"] = {"pre_gather": solo_pre / solo_tot, "gather": solo_ms / solo_tot,
+                                 "post_gather": solo_post / solo_tot,
+                                 "step_ms_one_in_flight": solo_tot / max(1, n_solo),
+                                 "note": "CUDA-event segments of the step with one query in "
+                                         "flight (serialised, comparable with "
+                                         "profiles/*launches*.csv)"}
+        out["step_share_overlapped"] = {"pre_gather": pre_ms / tot, "gather": gather_ms / tot,
+                                        "post_gather": post_ms / tot}
+        return out
+
+    # ---------------------------------------------------------------- e2e (host buffers)
+    def host_buffers(self):
+        from deeprecsys_b200.engine import pinned_empty
+        spec, B = self.spec, self.B
         T, L = spec.T, spec.L
-        h_idx, _k1 = pinned_empty((T, B * L), np.int32)
-        h_len, _k2 = pinned_empty((T, B), np.int32)
-        h_den, _k3 = pinned_empty((B, max(1, spec.m_den)), np.float32)
-        h_out, _k4 = pinned_empty((B, spec.out_dim), np.float32)
-        h_idx[:] = lS_i[0]; h_len[:] = lS_l[0]
+        h = {}
+        h["idx"], h["_k1"] = pinned_empty((T, B * L), np.int32)
+        h["len"], h["_k2"] = pinned_empty((T, B), np.int32)
+        h["den"], h["_k3"] = pinned_empty((B, max(1, spec.m_den)), np.float32)
+        h["out"], h["_k4"] = pinned_empty((B, spec.out_dim), np.float32)
+        for t in range(T):
+            h["idx"][t] = self.lS_i[0][t][:B * L]
+            h["len"][t] = self.lS_l[0][t][:B]
         if spec.m_den > 0:
-            h_den[:] = lX[0]
-        idx_ptrs = (C.c_void_p * T)(*[h_idx[t].ctypes.data for t in range(T)])
-        len_ptrs = (C.c_void_p * T)(*[h_len[t].ctypes.data for t in range(T)])
-        den_ptr = C.c_void_p(h_den.ctypes.data) if spec.m_den > 0 else None
-        out_ptr = C.c_void_p(h_out.ctypes.data)
+            h["den"][:] = self.lX[0][:B]
+        h["idx_ptrs"] = (C.c_void_p * T)(*[h["idx"][t].ctypes.data for t in range(T)])
+        h["len_ptrs"] = (C.c_void_p * T)(*[h["len"][t].ctypes.data for t in range(T)])
+        h["den_ptr"] = C.c_void_p(h["den"].ctypes.data) if spec.m_den > 0 else None
+        h["out_ptr"] = C.c_void_p(h["out"].ctypes.data)
+        return h
 
-        # every step: H2D of that step's ids/lengths/dense from pinned memory, kernels, D2H of
-        # the scores.  Steps are enqueued back to back; the engine's lanes overlap the copy of
-        # step i+1 with the kernels of step i (at most n_lanes steps in flight).
-        for _ in range(max(3, opts.warmup)):
-            eng.enqueue_host(den_ptr, idx_ptrs, 0, len_ptrs, B, out_ptr)
+    def measure_e2e(self, steps, warmup, h=None, int64_too=False):
+        """Every step: H2D of that step's ids/lengths/dense from pinned memory, kernels, D2H of the
+        scores.  Steps are enqueued back to back; the engine's lanes overlap the copy of step
+        i+1 with the kernels of step i (at most n_lanes steps in flight)."""
+        from deeprecsys_b200.engine import pinned_empty
+        env, eng, spec, B = self.env, self.eng, self.spec, self.B
+        T, L = spec.T, spec.L
+        h = h or self.host_buffers()
+        for _ in range(max(3, warmup)):
+            eng.enqueue_host(h["den_ptr"], h["idx_ptrs"], 0, h["len_ptrs"], B, h["out_ptr"])
         eng.sync()
-        barrier()
+        env.barrier()
         t0 = time.perf_counter()
-        for _ in range(opts.steps):
-            eng.enqueue_host(den_ptr, idx_ptrs, 0, len_ptrs, B, out_ptr)
+        for _ in range(steps):
+            eng.enqueue_host(h["den_ptr"], h["idx_ptrs"], 0, h["len_ptrs"], B, h["out_ptr"])
         eng.sync()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        h2d = B * (T * L * 4 + T * 4 + spec.m_den * 4)
-        d2h = B * spec.out_dim * 4
-        e2e = {"value": world * B * opts.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * dt / opts.steps, "ids_dtype": "int32",
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": env.world * B * steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": B * (T * L * 4 + T * 4 + spec.m_den * 4),
+               "d2h_bytes_per_step": B * spec.out_dim * 4,
+               "ms_per_step": 1e3 * dt / steps, "ids_dtype": "int32",
                "note": "per step H2D -> kernels -> D2H, steps pipelined over the engine lanes, "
                        "wall clock incl. final sync, max over ranks"}
-        # the same step with int64 ids, the dtype the reference's run_queues receives from
-        # np.array(list) (the Cast to int32 then runs on the GPU): twice the id bytes over PCIe
-        h_idx64, _k5 = pinned_empty((T, B * L), np.int64)
-        h_idx64[:] = lS_i[0]
-        idx64_ptrs = (C.c_void_p * T)(*[h_idx64[t].ctypes.data for t in range(T)])
-        n64 = max(5, opts.steps // 3)
-        for _ in range(3):
-            eng.enqueue_host(den_ptr, idx64_ptrs, 1, len_ptrs, B, out_ptr)
-        eng.sync()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n64):
-            eng.enqueue_host(den_ptr, idx64_ptrs, 1, len_ptrs, B, out_ptr)
-        eng.sync()
-        dt64 = max_over_ranks(time.perf_counter() - t0)
-        e2e["int64_ids"] = {"value": world * B * n64 / dt64, "unit": UNIT, "steps": n64,
-                            "h2d_bytes_per_step": B * (T * L * 8 + T * 4 + spec.m_den * 4)}
-        del h_idx64, _k5
-        # per-query latency at the reference's largest query size (1024), same path.
-        # NOTE: the first 1024 samples of the staged host batch (inferenceEngine.py:200-215)
-        q = min(1024, B)
-        idx_q = (C.c_void_p * T)(*[h_idx[t].ctypes.data for t in range(T)])
-        lat = []
-        for i in range(220):
+        if int64_too:
+            # the same step with int64 ids, the dtype the reference's run_queues receives from
+            # np.array(list) (the Cast to int32 then runs on the GPU): twice the id bytes over PCIe
+            h64, _k = pinned_empty((T, B * L), np.int64)
+            for t in range(T):
+                h64[t] = self.lS_i[0][t][:B * L]
+            p64 = (C.c_void_p * T)(*[h64[t].ctypes.data for t in range(T)])
+            n64 = max(5, steps // 3)
+            for _ in range(3):
+                eng.enqueue_host(h["den_ptr"], p64, 1, h["len_ptrs"], B, h["out_ptr"])
+            eng.sync()
+            env.barrier()
             t0 = time.perf_counter()
-            eng.enqueue_host(den_ptr, idx_q, 0, len_ptrs, q, out_ptr)
+            for _ in range(n64):
+                eng.enqueue_host(h["den_ptr"], p64, 1, h["len_ptrs"], B, h["out_ptr"])
+            eng.sync()
+            dt64 = env.max_over_ranks(time.perf_counter() - t0)
+            e2e["int64_ids"] = {"value": env.world * B * n64 / dt64, "unit": UNIT, "steps": n64,
+                                "h2d_bytes_per_step": B * (T * L * 8 + T * 4 + spec.m_den * 4)}
+        return e2e
+
+    def measure_latency(self, h, q=1024, n=220):
+        """Per-query wall latency at the reference's largest query size, host path.  The first
+        q samples of the staged host batch (inferenceEngine.py:200-215)."""
+        eng = self.eng
+        q = min(q, self.B)
+        lat = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            eng.enqueue_host(h["den_ptr"], h["idx_ptrs"], 0, h["len_ptrs"], q, h["out_ptr"])
             eng.sync()
             lat.append(time.perf_counter() - t0)
         lat = np.array(lat[20:]) * 1e3
-        latency = {"query_size": q, "p50_ms": float(np.percentile(lat, 50)),
-                   "p95_ms": float(np.percentile(lat, 95)),
-                   "p99_ms": float(np.percentile(lat, 99)),
-                   "inferences_per_s_at_p99": q / (float(np.percentile(lat, 99)) * 1e-3)}
+        return {"query_size": q, "p50_ms": float(np.percentile(lat, 50)),
+                "p95_ms": float(np.percentile(lat, 95)), "p99_ms": float(np.percentile(lat, 99)),
+                "inferences_per_s_at_p99": q / (float(np.percentile(lat, 99)) * 1e-3)}
 
-    # ---------------- batch-size sweep (staged path), reference sweep shape 4^0..4^5 + larger
-    sweep = None
-    if not opts.no_sweep and rank == 0 and not sharded:
+    def measure_sweep(self):
+        """Batch-size sweep (staged path): the reference's 4^0..4^5 (sweep_rt.py:160-174) + larger."""
+        eng, nb = self.eng, self.nb
         sweep = {}
         for bs in [1, 4, 16, 64, 256, 1024, 4096, 16384, 65536]:
-            if bs > B:
+            if bs > self.B:
                 continue
             iters = 30
             for i in range(3):
@@ -501,119 +660,314 @@ def run_b200(opts):
             for i in range(iters):
                 eng.enqueue_staged(i % nb, bs)
             ms = eng.timer_stop()
-            sweep[str(bs)] = {"ms_per_step": ms / iters, "inferences_per_s": bs * iters / (ms * 1e-3)}
-    barrier()
+            sweep[str(bs)] = {"ms_per_step": ms / iters,
+                              "inferences_per_s": bs * iters / (ms * 1e-3)}
+        return sweep
 
-    # ---------------- CPU baseline (rank 0, N=1 only)
-    cpu = None
-    if keep_host:
+    # ---------------------------------------------------------------- CPU baseline
+    def measure_cpu(self, seconds, n_cap):
         import torch
         torch.set_num_threads(len(os.sched_getaffinity(0)))
         from oracle.torch_cpu_engine import TorchCpuModel, time_forward
-        n = min(int(opts.cpu_sample), B)
-        model = TorchCpuModel(spec, host_tables, fcs)
-        dense = lX[0][:n] if spec.m_den > 0 else None
-        ids = [lS_i[0][t][: n * spec.L] for t in range(spec.T)]
-        lens = [lS_l[0][t][:n] for t in range(spec.T)]
-        v, reps, secs, threads = time_forward(model, dense, ids, lens,
-                                              min_seconds=opts.cpu_seconds,
-                                              max_seconds=3 * opts.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d reps x first %d samples of staged batch 0 (%.1f s of CPU work)"
-                         % (reps, n, secs),
-               "what": "torch-CPU port of the reference CPU engine net (embedding_bag + addmm)",
-               "host_cores_available": len(os.sched_getaffinity(0))}
+        spec = self.spec
+        n = min(int(n_cap), self.B)
+        tables = [self.host_tables[t] for t in range(spec.T)]
+        model = TorchCpuModel(spec, tables, self.fcs)
+        dense = self.lX[0][:n] if spec.m_den > 0 else None
+        ids = [self.lS_i[0][t][: n * spec.L] for t in range(spec.T)]
+        lens = [self.lS_l[0][t][:n] for t in range(spec.T)]
+        v, reps, secs, threads = time_forward(model, dense, ids, lens, min_seconds=seconds,
+                                              max_seconds=3 * seconds)
+        return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "%d reps x first %d samples of staged batch 0 (%.1f s of CPU work)"
+                          % (reps, n, secs),
+                "what": "torch-CPU port of the reference CPU engine net (embedding_bag + addmm)",
+                "host_cores_available": len(os.sched_getaffinity(0))}
 
-    hbm_allocated = eng.hbm_bytes()
-    eng.close()
+    # ---------------------------------------------------------------- in-bench parity
+    def parity(self, n_pick=48, batch_id=0):
+        """Sampled rows of one served step against oracle.numpy_oracle, outside every timed
+        region: pooled vectors BIT-EXACT (row-wise sharding: against the oracle's emulation of
+        the rank-order reduction), scores within the stated tolerance of the MLP precision.
+        The oracle works on compact copies of just the table rows the picked samples touch."""
+        from deeprecsys_b200 import _lib
+        from deeprecsys_b200 import shard as shardlib
+        from oracle import numpy_oracle as O
+        env, spec, eng, GB = self.env, self.spec, self.eng, self.GB
+        T, L = spec.T, spec.L
+        eng.enqueue_staged(batch_id, GB)
+        eng.sync()
+        pooled = eng.fetch_stage(_lib.STAGE_POOLED)          # rows held by this rank
+        out = eng.fetch_stage(_lib.STAGE_OUT)
+        if self.sharded:
+            row0, rows = shardlib.sample_slice(GB, env.rank, env.world)
+        else:
+            row0, rows = 0, GB
+        res = {"samples_checked": 0, "pooled": "skipped", "out_max_abs_err": None}
+        ok = True
+        if rows > 0 and spec.model_type != "dien":
+            pick = np.sort(np.random.RandomState(5 + env.rank).choice(
+                rows, size=min(n_pick, rows), replace=False))
+            g = pick + row0                                  # global sample ids
+            ids, small, lens, want_pooled = [], [], [], []
+            for t in range(T):
+                full_ids = np.asarray(self.lS_i[batch_id][t])
+                seg = full_ids.reshape(-1, L)[g].reshape(-1) if L > 0 else full_ids[:0]
+                uniq, inv = np.unique(seg, return_inverse=True)
+                W = (self.host_tables[t] if (self.host_tables is not None and t in self.host_tables)
+                     else synth_table(spec, self.tseed, t))
+                lt = np.ascontiguousarray(np.asarray(self.lS_l[batch_id][t])[g])
+                if self.row_mode:
+                    # the rank-order emulation needs global row ids: pool on the full table
+                    want_pooled.append(O.sparse_lengths_sum_rowwise(W, seg, lt, env.world))
+                small.append(np.ascontiguousarray(W[uniq]))
+                ids.append(inv.astype(np.int64))
+                lens.append(lt)
+                del W
+            dense = self.lX[batch_id][g] if spec.m_den > 0 else None
+            st = O.forward(spec, small, self.fcs, dense, ids, lens)
+            got_p, got_o = pooled[pick], out[pick]
+            if self.row_mode:
+                want_p = np.concatenate(want_pooled, axis=1)
+                res["pooled"] = ("bit-exact (rank-order emulation)"
+                                 if np.array_equal(got_p.view(np.uint32), want_p.view(np.uint32))
+                                 else "MISMATCH")
+                ok = ok and np.allclose(got_p, st["pooled"], rtol=1e-5, atol=1e-6)
+            else:
+                res["pooled"] = ("bit-exact" if np.array_equal(got_p.view(np.uint32),
+                                                               st["pooled"].view(np.uint32))
+                                 else "MISMATCH")
+            err = float(np.max(np.abs(got_o - st["out"]))) if got_o.size else 0.0
+            tol = {"fp32": 1e-5, "tf32x3": 5e-5, "tf32": 5e-3}[self.opts.precision]
+            if self.row_mode:
+                tol = max(tol, 1e-4)
+            scale = max(1.0, float(np.max(np.abs(st["out"]))) if st["out"].size else 1.0)
+            res.update({"samples_checked": int(len(pick)), "out_max_abs_err": err,
+                        "out_tolerance": tol * scale})
+            ok = ok and res["pooled"] != "MISMATCH" and err <= tol * scale
+        res["ok"] = bool(ok)
+        return res
 
-    # ---------------- system level: the metric's "at p99 latency" half (rank 0, N=1 only).
-    # accelInferenceEngine as a separate process behind the reference's Queue protocol, Poisson
-    # arrivals, query sizes normal(256, 32) clipped to [1, 1024] (run_DeepRecInfra.sh:34-37).
+
+# ----------------------------------------------------------------------------
+def run_secondary(env, opts, name, B):
+    """One of the other BASELINE configs on one GPU: value / e2e / cpu_baseline / roofline /
+    parity, each figure the same definition as the headline's."""
+    t_start = time.time()
+    nb = 2
+    steps = max(5, min(opts.steps, 20))
+    w = Workload(env, opts, name, B, nb, keep_host=not opts.no_cpu_baseline)
+    try:
+        val = w.measure_value(steps, opts.warmup, clocks=True, min_load_ms=350.0)
+        solo = w.measure_solo(4)
+        out = {"config": {"workload": workload_text(name, w.spec, B), "mlp_precision": opts.precision,
+                          "lanes": w.lanes},
+               "value": val["value"], "unit": UNIT, "ms_per_step": val["ms_per_step"],
+               "steps": steps, "gpu_launches": val["launches"], "clocks": val.get("clocks"),
+               "roofline": w.roofline(val, solo)}
+        if not opts.no_e2e:
+            out["e2e"] = w.measure_e2e(steps, opts.warmup)
+        out["parity"] = w.parity()
+        if not opts.no_cpu_baseline:
+            out["cpu_baseline"] = w.measure_cpu(min(3.0, opts.cpu_seconds), 1024)
+        out["hbm_bytes_allocated"] = w.eng.hbm_bytes()
+    finally:
+        w.close()
+    out["wall_s"] = time.time() - t_start
+    return out
+
+
+def run_sharded_leg(env, opts, config, mode):
+    """config table-/row-sharded across all ranks of the job (north_star; BASELINE config 3 for
+    rm3): one global model, every step a query of B*world samples that ALL ranks serve together —
+    rank r gathers its tables (or its row slices) for every sample and K1 stores the pooled
+    vectors straight into the owning rank's interaction buffer over NVLink; the MLPs run on the
+    rank's own B samples."""
+    t_start = time.time()
+    steps = max(5, opts.steps)
+    w = Workload(env, opts, config, int(opts.batch), 2, shard=mode)
+    try:
+        par = w.parity()
+        par["ok"] = env.all_ok(par["ok"])
+        val = w.measure_value(steps, opts.warmup, clocks=True, min_load_ms=400.0)
+        solo = w.measure_solo(4)
+        roof = w.roofline(val, solo)
+        out = {"config": {"workload": workload_text(config, w.spec, w.GB),
+                          "global_batch": w.GB,
+                          "parallelism": "%s-sharded x%d, exchange fused into K1 (peer stores over "
+                                         "NVLink), flag barrier" % (mode, env.world),
+                          "mlp_precision": opts.precision, "lanes": w.lanes},
+               "value": val["value"], "unit": UNIT, "ms_per_step": val["ms_per_step"],
+               "steps": steps, "gpu_launches": val["launches"],
+               "parity": ("bit-exact" if (par["ok"] and not w.row_mode) else
+                          "bit-exact vs rank-order emulation" if par["ok"] else "FAILED"),
+               "parity_detail": env.gather_objects(par),
+               "roofline": roof, "clocks": val.get("clocks"),
+               "clocks_all_ranks": env.gather_objects(val.get("clocks")),
+               "exchange_bytes_per_step": w.GB * w.spec.T * w.spec.D * 4
+               * (env.world if w.row_mode else 1)}
+    finally:
+        w.close()
+    out["wall_s"] = time.time() - t_start
+    return out
+
+
+def run_system(env, opts):
+    """The metric's "at p99 latency" half (one generator + engine process pair per GPU).
+    accelInferenceEngine as a separate process behind the reference's Queue protocol, Poisson
+    arrivals, query sizes normal(256, 32) clipped to [1, 1024] (run_DeepRecInfra.sh:34-37)."""
     system, res = None, None
-    if not opts.no_system and opts.config == "rm1" and not sharded:
-        # a fresh interpreter: the harness forks the engine process (as DeepRecSys.py does), and
-        # a forked child cannot use CUDA once its parent — this process — has initialised it
-        cfg = os.path.join(ROOT, "deeprecsys_b200", "models", "configs", CONFIGS[opts.config])
-        cmd = [sys.executable, "-m", "deeprecsys_b200.serve", "--config_file", cfg,
-               "--num_batches", "32", "--max_mini_batch_size", "1024",
-               "--batch_size_distribution", "normal", "--avg_mini_batch_size", "256",
-               "--var_mini_batch_size", "32", "--model_accel", "--queue",
-               "--numpy_rand_seed", str(opts.seed + rank), "--accel_precision", opts.precision,
-               "--accel_device", str(local),
-               "--serve_rates_ms", opts.system_rates_ms,
-               "--serve_queries", str(opts.system_queries)]
-        try:
-            proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                                  text=True, timeout=900)
-            sys.stderr.write(proc.stderr[-2000:])
-            res = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
-        except Exception as exc:            # the serving leg must not cost the bench line
-            system = {"error": repr(exc)}
-    if dist is not None and not opts.no_system and opts.config == "rm1" and not sharded:
-        # N > 1: one (load generator, engine process) pair per GPU, run side by side; the job's
-        # figure is the sum of the pairs' throughputs at the largest of their p99s
-        allres = [None] * world
-        dist.all_gather_object(allres, res)
-        if rank == 0 and all(r and r["best"] for r in allres):
+    # a fresh interpreter: the harness forks the engine process (as DeepRecSys.py does), and a
+    # forked child cannot use CUDA once its parent — this process — has initialised it
+    cfg = os.path.join(CONFIG_DIR, CONFIGS[opts.config])
+    cmd = [sys.executable, "-m", "deeprecsys_b200.serve", "--config_file", cfg,
+           "--num_batches", "32", "--max_mini_batch_size", "1024",
+           "--batch_size_distribution", "normal", "--avg_mini_batch_size", "256",
+           "--var_mini_batch_size", "32", "--model_accel", "--queue",
+           "--numpy_rand_seed", str(opts.seed + env.rank), "--accel_precision", opts.precision,
+           "--accel_device", str(env.local), "--serve_queries", str(opts.system_queries)]
+    if opts.system_rates_ms:
+        cmd += ["--serve_rates_ms", opts.system_rates_ms]
+    try:
+        proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True, timeout=900)
+        sys.stderr.write(proc.stderr[-2000:])
+        res = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception as exc:            # the serving leg must not cost the bench line
+        system = {"error": repr(exc)}
+    if env.dist is not None:
+        # N > 1: the pairs run side by side; the job's figure is the sum of the pairs'
+        # throughputs at the largest of their p99s
+        allres = env.gather_objects(res)
+        if env.rank == 0 and all(r and r["best"] for r in allres):
             bests = [r["best"] for r in allres]
             res = {"target_p99_ms": allres[0]["target_p99_ms"], "runs": [r["runs"] for r in allres],
+                   "engine": allres[0].get("engine"),
                    "best": {"inferences_per_s": sum(b["inferences_per_s"] for b in bests),
                             "qps": sum(b["qps"] for b in bests),
                             "p99_ms": max(b["p99_ms"] for b in bests),
                             "p95_ms": max(b["p95_ms"] for b in bests)}}
-        elif rank == 0:
+        elif env.rank == 0:
             res = None
             system = {"error": "a rank's serving run failed or missed the p99 target"}
-    if res and rank == 0:
+    if res and env.rank == 0:
         best = res["best"]
         system = {"what": "accelInferenceEngine process behind multiprocessing Queues "
                           "(ServiceRequest in, ServiceResponse out), Poisson arrivals, query "
                           "sizes normal(256,32) in [1,1024], 32 pre-generated batches; latency = "
                           "inference_end_time - arrival_time (DeepRecSys.py:122-123); one "
                           "generator + engine pair per GPU",
-                  "pairs": world,
+                  "pairs": env.world, "engine": res.get("engine"),
                   "target_p99_ms": res["target_p99_ms"],
                   "inferences_per_s_at_p99": best["inferences_per_s"] if best else None,
                   "qps": best["qps"] if best else None,
                   "p99_ms": best["p99_ms"] if best else None,
                   "p95_ms": best["p95_ms"] if best else None,
                   "runs": res["runs"]}
+    return system
+
+
+def run_b200(opts):
+    env = Env()
+    rank, world = env.rank, env.world
+    from deeprecsys_b200.engine import bind_to_device_numa_node
+
+    # one process per GPU: sit on the GPU's NUMA node before any pinned buffer is allocated
+    numa_node = bind_to_device_numa_node(env.local) if world > 1 else -1
+
+    B, nb = int(opts.batch), int(opts.staged_batches)
+    keep_host = (rank == 0 and world == 1 and not opts.no_cpu_baseline)
+    w = Workload(env, opts, opts.config, B, nb, shard=opts.shard, keep_host=keep_host)
+    spec, sharded = w.spec, w.sharded
+
+    # ---------------- value: inputs resident in HBM, device-timed
+    val = w.measure_value(opts.steps, opts.warmup, clocks=True)
+    # ---------------- roofline of the dominant kernel (K1 gather), same timed region
+    solo = w.measure_solo(8)
+    roofline = w.roofline(val, solo)
+
+    # ---------------- e2e: C-ABI with pinned HOST buffers, H2D + D2H inside
+    e2e, latency = None, None
+    if not opts.no_e2e and not sharded:
+        h = w.host_buffers()
+        e2e = w.measure_e2e(opts.steps, opts.warmup, h, int64_too=True)
+        latency = w.measure_latency(h)
+        del h
+
+    sweep = None
+    if not opts.no_sweep and rank == 0 and not sharded:
+        sweep = w.measure_sweep()
+    env.barrier()
+
+    parity = w.parity() if opts.config != "dien" else None
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu = w.measure_cpu(opts.cpu_seconds, opts.cpu_sample) if keep_host else None
+
+    hbm_allocated = w.eng.hbm_bytes()
+    w.close()
+    del w
+
+    # ---------------- the other BASELINE configs (N = 1)
+    secondary = None
+    if world == 1 and not opts.no_secondary and opts.config == "rm1":
+        only = set(opts.secondary.split(",")) if opts.secondary else None
+        secondary = {}
+        for name, sb in SECONDARY:
+            if only is not None and name not in only:
+                continue
+            try:
+                secondary[name] = run_secondary(env, opts, name, sb)
+            except Exception as exc:            # one config must not cost the bench line
+                secondary[name] = {"error": repr(exc)}
+
+    # ---------------- the sharded data path (N > 1)
+    shard_legs = None
+    if world > 1 and not opts.no_sharded and opts.config == "rm1" and not sharded:
+        shard_legs = {}
+        for item in [s for s in opts.sharded.split(",") if s]:
+            config, mode = item.split(":")
+            key = mode if config == "rm1" else "%s_%s" % (config, mode)
+            try:
+                leg = run_sharded_leg(env, opts, config, mode)
+            except Exception as exc:
+                leg = {"error": repr(exc)}
+            failed = not env.all_ok("error" not in leg)
+            if failed and "error" not in leg:
+                leg = {"error": "another rank failed this leg"}
+            shard_legs[key] = leg
+            if failed:
+                break                           # ranks may be out of lockstep: stop here
+        if "table" in shard_legs and "value" in shard_legs["table"]:
+            shard_legs["table"]["vs_replica"] = shard_legs["table"]["value"] / val["value"]
+        if "row" in shard_legs and "value" in shard_legs["row"]:
+            shard_legs["row"]["vs_replica"] = shard_legs["row"]["value"] / val["value"]
+
+    # ---------------- system level
+    system = None
+    if not opts.no_system and opts.config == "rm1" and not sharded:
+        system = run_system(env, opts)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-            "steps": opts.steps, "warmup": max(3, opts.warmup), "ms_per_step": ms_per_step,
+            "metric": METRIC, "value": val["value"], "unit": UNIT, "n_gpus": world,
+            "steps": opts.steps, "warmup": max(3, opts.warmup), "ms_per_step": val["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             # the arithmetic the path computes in: the gather/interaction are fp32; the MLP is
             # fp32 FFMA, or tcgen05 TF32 tensor-core products — "tf32x3" = 3-pass error-compensated
             # (results within 1e-5 of fp32), "tf32" = single pass
             "dtype": "f32" if opts.precision == "fp32" else "f32+" + opts.precision,
             "data": "synthetic",
-            "config": {"workload": "dlrm_%s (%s) %d tables x %s rows x D=%d, L=%d, "
-                                   "%d samples/step (=%d coalesced 1024-item queries), "
-                                   "staged in HBM" % (opts.config, spec.interaction_op, spec.T,
-                                                     spec.table_rows[0], spec.D, spec.L, B,
-                                                     max(1, B // 1024)),
-                       "global_batch": B * world,
-                       "parallelism": ("%s-sharded x%d (K1 peer stores over NVLink)"
-                                       % (opts.shard, world) if sharded else "replica x%d" % world),
-                       "l2_policy": "inputs larger than L2 (4.1 GB tables, %s; "
-                                    "%d staged batches cycled)"
-                                    % ("LRU stack-distance ids%s, profile %s"
-                                       % (" sorted inside each lookup" if opts.locality_sorted
-                                          else "", opts.locality)
-                                       if opts.locality else "uniform ids", nb),
-                       "mlp_precision": opts.precision, "lanes": opts.lanes,
-                       "numa_node": numa_node},
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "config": headline_config(opts, spec, B, world, sharded), "numa_node": numa_node,
+            "clocks": val.get("clocks"), "gpu_launches": val["launches"],
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "latency_1024": latency, "sweep": sweep, "system": system,
+            "secondary": secondary, "sharded": shard_legs,
             "hbm_bytes_allocated": hbm_allocated,
         }
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.destroy_process_group()
     return 0
 
 
