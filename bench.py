@@ -96,9 +96,9 @@ def parse_args():
                    help="N>1: comma list of config:mode sharded legs")
     p.add_argument("--no_system", action="store_true",
                    help="skip the Poisson-arrival serving run through the Queue API")
-    p.add_argument("--system_rates_ms", type=str, default=None,
+    p.add_argument("--system_rates_ms", type=str, default="0.5,0.125,0.09,0.06,0.045",
                    help="mean inter-arrival times (ms) of the serving run")
-    p.add_argument("--system_queries", type=int, default=4000)
+    p.add_argument("--system_queries", type=int, default=2000)
     p.add_argument("--seed", type=int, default=123)
     p.add_argument("--locality", type=str, default=None,
                    help="ids with temporal reuse instead of uniform-random ones: a stack-distance "

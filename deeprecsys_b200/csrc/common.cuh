@@ -85,11 +85,24 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // ------------------------------------------------------------ global loads
 // Embedding rows are touched once per query (uniform ids over GBs of table):
 // read-only path, do not allocate in L1.
+// DRS_ROW_EVICT_FIRST (probe builds, tools/k1_probe.cu): additionally mark the row's L2 line
+// evict-first, so that streamed rows do not push ids / activations / weights out of L2.
+#ifndef DRS_ROW_EVICT_FIRST
+#define DRS_ROW_EVICT_FIRST 0
+#endif
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   float4 v;
+#if DRS_ROW_EVICT_FIRST
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+#else
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
+#endif
   return v;
 }
 

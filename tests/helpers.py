@@ -62,6 +62,13 @@ SMALL = {
                  "--user_behavior_tables", "10", "--arch_sparse_feature_size", "32",
                  "--arch_mlp_bot", "8-4", "--arch_mlp_top", "200-80-2",
                  "--arch_interaction_op", "cat", "--num_indices_per_lookup", "3"],
+    # DIN as the reference's cli() expands it when din.json's values arrive as FLAGS rather than
+    # through the JSON (utils/utils.py:132-149): profile + 251 behaviour tables + ad + context
+    # = 254 tables, 251 attention units [3D, 1, D] ("pure-CLI variant")
+    "din254": ["--model_type", "din", "--arch_embedding_size", "1000-100-2000-2000",
+               "--user_behavior_tables", "250", "--arch_sparse_feature_size", "32",
+               "--arch_mlp_bot", "1", "--arch_mlp_top", "200-80-2",
+               "--arch_interaction_op", "cat", "--num_indices_per_lookup", "3"],
 }
 
 
