@@ -20,7 +20,7 @@ MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE, MLP_RNN_BASE = 0, 1, 
 (STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS, STAGE_TASK,
  STAGE_IDS) = range(8)
 SHARD_TABLE, SHARD_ROW = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 SHARD_BLOB_BYTES = 192
 
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
@@ -80,6 +80,8 @@ _SIGNATURES = {
                                     C.POINTER(C.c_int64)]),
     "drs_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int, C.c_void_p,
                                   C.POINTER(C.c_int64)]),
+    "drs_submit_many": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.c_void_p, C.POINTER(C.c_int64)]),
     "drs_wait": (C.c_int, [C.c_void_p, C.c_int64]),
     "drs_lane_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "drs_timer_start": (C.c_int, [C.c_void_p]),

@@ -60,8 +60,18 @@ class AccelBackend(object):
         gen = DLRMDataGenerator(args)
         (self.nbatches, self.lX, self.lS_l, self.lS_i) = gen.generate_input_data()
         (_, self.lT) = gen.generate_output_data()          # consumes the RNG like the CPU engine
+        # coalesced serving stacks several queued requests into one launch: the engine's
+        # activation buffers hold accel_stack_rows samples (a staged batch still holds
+        # max_mini_batch_size)
+        self.coalesce = max(1, int(getattr(args, "accel_coalesce", 1) or 1))
+        cap = int(args.max_mini_batch_size)
+        if self.coalesce > 1:
+            cap = max(cap, int(getattr(args, "accel_stack_rows", 0) or 0))
         self.engine = AccelEngine(args=args, device=int(getattr(args, "accel_device", 0)),
-                                  max_batch=int(args.max_mini_batch_size))
+                                  max_batch=cap, lanes=int(getattr(args, "accel_lanes", 0) or 0),
+                                  max_lookups_per_table=int(args.max_mini_batch_size)
+                                  * max(1, int(args.num_indices_per_lookup)))
+        self.stack_rows = cap
         self.engine.create()                               # tables -> MLPs, reference draw order
         self.spec = self.engine.spec
         self.upload = bool(getattr(args, "accel_upload_inputs", False))
@@ -127,8 +137,8 @@ class AccelBackend(object):
         import ctypes
         if not hasattr(self, "_out_pool"):
             from deeprecsys_b200.engine import pinned_empty
-            self._out_pool = [pinned_empty((int(self.args.max_mini_batch_size), self.spec.out_dim),
-                                           np.float32) for _ in range(self.depth)]
+            self._out_pool = [pinned_empty((self.engine.max_batch, self.spec.out_dim), np.float32)
+                              for _ in range(self.depth + 1)]
             self._out_next = 0
         buf, _owner = self._out_pool[self._out_next]
         self._out_next = (self._out_next + 1) % len(self._out_pool)
@@ -143,6 +153,17 @@ class AccelBackend(object):
         else:
             ticket = self.engine.submit_staged(batch_id, int(batch_size), out_ptr)
         return ("ticket", ticket, buf, int(batch_size))
+
+    def submit_many(self, batch_ids, batch_sizes):
+        """Several queued requests as ONE stacked launch (drs_submit_many); rows of request k
+        start at sum(batch_sizes[:k]) of the completed buffer."""
+        buf, out_ptr = self._next_out()
+        ticket = self.engine.submit_many(batch_ids, batch_sizes, out_ptr)
+        return ("ticket", ticket, buf, int(sum(batch_sizes)))
+
+    @property
+    def can_coalesce(self):
+        return self.coalesce > 1 and not self.upload
 
     # requests that bring their own tensors (utils.packets.TensorServiceRequest) ----------------
     def _attach_ring(self, desc):
@@ -403,12 +424,44 @@ def _wait_for_siblings(siblings, requestQueue, responseQueue, engine_id, args):
                                      exp_packet=request.exp_packet, sub_id=request.sub_id))
 
 
+def _spawn_responder(args, responseQueue, engine_id, multi):
+    """Fork the responder helper (utils/response_ring.py) BEFORE this process touches CUDA.
+    Returns (ring, process) or (None, None): several consumers on one queue, a non-stock queue,
+    or --accel_responder 0 keep the responses in-process."""
+    if multi or not int(getattr(args, "accel_responder", 0) or 0):
+        return None, None
+    if int(getattr(args, "accel_coalesce", 1) or 1) <= 1:
+        return None, None
+    from deeprecsys_b200.utils.fastqueue import FrameWriter
+    if not FrameWriter(responseQueue).fast:
+        return None, None
+    try:
+        import multiprocessing as mp
+        from deeprecsys_b200.utils.response_ring import ResponseRing, responder_main
+        ring = ResponseRing()
+        cur = mp.current_process()
+        was_daemon = cur._config.get("daemon")
+        cur._config["daemon"] = False          # DeepRecSys.py:71 marks engines daemonic
+        try:
+            proc = mp.get_context("fork").Process(
+                target=responder_main, args=(ring, responseQueue, engine_id, ServiceResponse))
+            proc.start()
+        finally:
+            cur._config["daemon"] = was_daemon
+        return ring, proc
+    except Exception as exc:
+        print("[Accel] responder helper unavailable (%r); responses stay in-process" % (exc,))
+        return None, None
+
+
 def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):
     np.random.seed(args.numpy_rand_seed)
     np.set_printoptions(precision=args.print_precision)
 
     siblings, sibling_ready = ([], None) if sibling else _spawn_siblings(
         args, requestQueue, engine_id, responseQueue)
+    multi = sibling or bool(siblings)
+    resp_ring, responder = _spawn_responder(args, responseQueue, engine_id, multi)
 
     backend, failure = None, None
     if args.model_name not in SUPPORTED_MODEL_NAMES:
@@ -446,71 +499,110 @@ def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibli
     # default -> responses would leave up to 5 ms late exactly when the engine is loaded
     sys.setswitchinterval(1e-4)
 
-    # Packets are served in arrival order with up to ``depth`` of them in flight on the GPU;
-    # a response is stamped when its own result has landed in host memory.
+    # Packets are served in arrival order with up to ``depth`` launches in flight on the GPU; a
+    # launch serves ONE request, or — coalesced serving — every plain request that was already
+    # waiting when the loop came back to the queue (up to --accel_coalesce of them, at most
+    # --accel_stack_rows samples).  A response is stamped when its own result has landed in host
+    # memory.
     import collections
-    put_response = _direct_put(responseQueue)
-    inflight = collections.deque()
+    from deeprecsys_b200.utils.fastqueue import FrameReader, FrameWriter
+    from deeprecsys_b200.utils.response_ring import KIND_SENTINEL, encode_request
+    writer = FrameWriter(responseQueue)
+    reader = None if multi else FrameReader(requestQueue)      # sole consumer: batched pipe reads
+    inflight = collections.deque()         # (entries [(request, start_time)], handle, sizes | None)
+    pending = collections.deque()          # pulled from the queue, not yet submitted
     pipelined = backend is not None and hasattr(backend, "submit") and backend.depth > 1
     depth = backend.depth if pipelined else 1
+    coalesce = 1
+    if (pipelined and not multi and hasattr(backend, "submit_many")
+            and getattr(backend, "can_coalesce", True)):
+        coalesce = max(1, int(getattr(args, "accel_coalesce", 1) or 1))
+    stack_rows = int(getattr(backend, "stack_rows", 0) or getattr(args, "max_mini_batch_size", 0))
+
+    def respond_many(entries, out_sizes):
+        """One response per request; out_sizes[i] = rows answered for entries[i] (0 = failed)."""
+        end_time = time.time()
+        debugPrint(args, "Accel", "Sending response back")
+        rows, plain = [], []
+        ring_ok = resp_ring is not None and responder.is_alive()
+        for (request, start_time), out_bs in zip(entries, out_sizes):
+            enc = encode_request(request) if ring_ok else None
+            if enc is None:
+                plain.append(ServiceResponse(consumer_id=engine_id,
+                                             epoch=request.epoch,
+                                             batch_id=request.batch_id,
+                                             batch_size=request.batch_size,
+                                             arrival_time=request.arrival_time,
+                                             process_start_time=start_time,
+                                             queue_end_time=end_time,
+                                             inference_end_time=end_time,
+                                             out_batch_size=out_bs,
+                                             total_sub_batches=request.total_sub_batches,
+                                             exp_packet=request.exp_packet,
+                                             sub_id=request.sub_id))
+            else:
+                vals, kinds, at = enc
+                rows.append(vals[:5] + (int(out_bs), vals[5], kinds, at, start_time, end_time))
+        if rows:
+            resp_ring.push(rows)
+        if plain:
+            writer.put_many(plain)
+
+    def dump(request, out):
+        if backend.dump_dir:
+            np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (
+                request.epoch, request.batch_id, request.batch_size)), np.array(out))
 
     def finish_oldest():
-        request, start_time, handle = inflight.popleft()
-        out_batch_size = 0
+        entries, handle, sizes = inflight.popleft()
         try:
             out = backend.complete(handle)
-            out_batch_size = int(out.shape[0])
-            if backend.dump_dir:
-                np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (
-                    request.epoch, request.batch_id, request.batch_size)), np.array(out))
+            if sizes is None:              # one request
+                out_sizes = [int(out.shape[0])]
+                dump(entries[0][0], out)
+            else:                          # coalesced: rows of request k start at sum(sizes[:k])
+                out_sizes, row = list(sizes), 0
+                if int(out.shape[0]) != sum(sizes):
+                    raise RuntimeError("coalesced launch returned %d rows for %d"
+                                       % (out.shape[0], sum(sizes)))
+                if backend.dump_dir:
+                    for (request, _), n in zip(entries, sizes):
+                        dump(request, out[row:row + n])
+                        row += n
         except Exception as exc:           # keep serving: the parent counts responses
             print("[Accel] request failed: %r" % (exc,))
             sys.stdout.flush()
-        respond(request, start_time, out_batch_size)
+            out_sizes = [0] * len(entries)
+        respond_many(entries, out_sizes)
 
-    def respond(request, start_time, out_batch_size):
-        end_time = time.time()
-        response = ServiceResponse(consumer_id=engine_id,
-                                   epoch=request.epoch,
-                                   batch_id=request.batch_id,
-                                   batch_size=request.batch_size,
-                                   arrival_time=request.arrival_time,
-                                   process_start_time=start_time,
-                                   queue_end_time=end_time,
-                                   inference_end_time=end_time,
-                                   out_batch_size=out_batch_size,
-                                   total_sub_batches=request.total_sub_batches,
-                                   exp_packet=request.exp_packet,
-                                   sub_id=request.sub_id)
-        debugPrint(args, "Accel", "Sending response back")
-        put_response(response)
+    def pull(block):
+        """Move what is waiting on the queue into ``pending``; -> True if anything arrived."""
+        debugPrint(args, "Accel", "Trying to pull request")
+        if reader is not None:
+            got = reader.drain(block=block)
+        else:
+            # several processes on one queue: a request seen by empty() may be taken by
+            # somebody else, so never block while a packet is in flight, and take one at a time
+            import queue as _queue
+            try:
+                got = [requestQueue.get() if block else requestQueue.get(block=False)]
+            except _queue.Empty:
+                got = []
+        if not got:
+            return False
+        now = time.time()
+        pending.extend((r, now) for r in got)
+        debugPrint(args, "Accel", "Pulled request")
+        return True
 
-    multi = sibling or bool(siblings)
-    request_waiting = _readable_probe(requestQueue)
-    import queue as _queue
     while True:
         if len(inflight) >= depth:
             finish_oldest()
             continue
-        debugPrint(args, "Accel", "Trying to pull request")
-        if inflight:
-            # never block on the queue while a packet is in flight: with sibling processes on
-            # the same queue a request seen by empty() may be taken by somebody else, and the
-            # in-flight packet's response would wait for the next arrival
-            if request_waiting is not None and not multi:
-                if not request_waiting():  # sole consumer: a readable pipe holds a whole packet
-                    finish_oldest()
-                    continue
-                request = requestQueue.get()
-            else:
-                try:
-                    request = requestQueue.get(block=False)
-                except _queue.Empty:
-                    finish_oldest()
-                    continue
-        else:
-            request = requestQueue.get()
-        debugPrint(args, "Accel", "Pulled request")
+        if not pending and not pull(block=not inflight):
+            finish_oldest()                # nothing waiting: complete the oldest launch instead
+            continue
+        request, start_time = pending[0]
 
         if request is None:
             # With several processes on one queue the sentinel keeps circulating: whoever takes it
@@ -526,29 +618,65 @@ def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibli
             for p in siblings:             # their responses must precede the final sentinel
                 p.join(timeout=120)
             debugPrint(args, "Accel", "Sending final done signal")
-            put_response(None)
+            if resp_ring is not None and responder.is_alive():
+                resp_ring.push([(0, 0, 0, 0, 0, 0, 0, KIND_SENTINEL, 0.0, 0.0, 0.0)])
+                responder.join(timeout=120)    # it forwards the sentinel after the last response
+            else:
+                writer.put(None)
             return
 
-        start_time = time.time()
         if backend is None:
-            respond(request, start_time, 0)
+            pending.popleft()
+            respond_many([(request, start_time)], [0])
             continue
+
+        # ---- coalesced launch: every plain request that is already here
+        if coalesce > 1 and not _carries_inputs(request):
+            group, sizes, rows = [], [], 0
+            while pending and len(group) < coalesce:
+                r, st = pending[0]
+                if r is None or _carries_inputs(r):
+                    break
+                try:
+                    n = int(r.batch_size)
+                except (TypeError, ValueError):
+                    break
+                if n < 1 or (group and rows + n > stack_rows):
+                    break
+                group.append((r, st))
+                sizes.append(n)
+                rows += n
+                pending.popleft()
+            if len(group) > 1:
+                try:
+                    handle = backend.submit_many([int(r.batch_id) for r, _ in group], sizes)
+                    inflight.append((group, handle, sizes))
+                except Exception as exc:
+                    print("[Accel] coalesced launch refused (%r); serving one by one" % (exc,))
+                    sys.stdout.flush()
+                    for entry in reversed(group):
+                        pending.appendleft(entry)
+                    coalesce = 1
+                continue
+            if group:
+                pending.appendleft(group[0])   # a single request: the ordinary path below
+                request, start_time = group[0]
+
+        pending.popleft()
         try:
             if pipelined:
-                inflight.append((request, start_time,
+                inflight.append(([(request, start_time)],
                                  backend.submit_inputs(request) if _carries_inputs(request)
-                                 else backend.submit(request.batch_id, request.batch_size)))
+                                 else backend.submit(request.batch_id, request.batch_size), None))
                 continue
             if _carries_inputs(request):
                 out = backend.serve_inputs(request)
             else:
                 out = backend.serve(request.batch_id, request.batch_size)
             out_batch_size = int(out.shape[0])
-            if backend.dump_dir:
-                np.save(os.path.join(backend.dump_dir, "accel_e%s_b%s_n%s.npy" % (
-                    request.epoch, request.batch_id, request.batch_size)), out)
+            dump(request, out)
         except Exception as exc:           # keep serving: the parent counts responses
             print("[Accel] request failed: %r" % (exc,))
             sys.stdout.flush()
             out_batch_size = 0
-        respond(request, start_time, out_batch_size)
+        respond_many([(request, start_time)], [out_batch_size])

@@ -471,37 +471,41 @@ int launch_gather_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid
   return DRS_OK;
 }
 
-template <int LPR, bool SHORT>
+template <int LPR, bool SHORT, bool MULTI>
 int launch_gather_persist_t(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int grid,
                             size_t smem) {
   static std::atomic<uint64_t> attr_set{0};
   if (first_use_on_device(attr_set))
-    CU(cudaFuncSetAttribute(k_sls_gather_persist<LPR, SHORT>,
+    CU(cudaFuncSetAttribute(k_sls_gather_persist<LPR, SHORT, MULTI>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  k_sls_gather_persist<LPR, SHORT><<<grid, kSlsThreads, smem, st>>>(p);
+  k_sls_gather_persist<LPR, SHORT, MULTI><<<grid, kSlsThreads, smem, st>>>(p);
   CU(cudaGetLastError());
   e->launches += 1;
   return DRS_OK;
 }
 
-template <bool SHORT>
+template <bool SHORT, bool MULTI>
 int launch_gather_persist_s(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
                             size_t smem) {
   switch (lpr) {
-    case 1:  return launch_gather_persist_t<1, SHORT>(e, st, p, grid, smem);
-    case 2:  return launch_gather_persist_t<2, SHORT>(e, st, p, grid, smem);
-    case 4:  return launch_gather_persist_t<4, SHORT>(e, st, p, grid, smem);
-    case 8:  return launch_gather_persist_t<8, SHORT>(e, st, p, grid, smem);
-    case 16: return launch_gather_persist_t<16, SHORT>(e, st, p, grid, smem);
-    default: return launch_gather_persist_t<32, SHORT>(e, st, p, grid, smem);
+    case 1:  return launch_gather_persist_t<1, SHORT, MULTI>(e, st, p, grid, smem);
+    case 2:  return launch_gather_persist_t<2, SHORT, MULTI>(e, st, p, grid, smem);
+    case 4:  return launch_gather_persist_t<4, SHORT, MULTI>(e, st, p, grid, smem);
+    case 8:  return launch_gather_persist_t<8, SHORT, MULTI>(e, st, p, grid, smem);
+    case 16: return launch_gather_persist_t<16, SHORT, MULTI>(e, st, p, grid, smem);
+    default: return launch_gather_persist_t<32, SHORT, MULTI>(e, st, p, grid, smem);
   }
 }
 
-// short segments take the multi-segment path
+// short segments take the multi-segment path; p.pk.n > 0 selects the coalesced-request tiles
 int launch_gather_persist(drs_engine* e, cudaStream_t st, const SlsLaunch& p, int lpr, int grid,
                           size_t smem) {
-  if (p.short_seg) return launch_gather_persist_s<true>(e, st, p, lpr, grid, smem);
-  return launch_gather_persist_s<false>(e, st, p, lpr, grid, smem);
+  if (p.pk.n > 0) {
+    if (p.short_seg) return launch_gather_persist_s<true, true>(e, st, p, lpr, grid, smem);
+    return launch_gather_persist_s<false, true>(e, st, p, lpr, grid, smem);
+  }
+  if (p.short_seg) return launch_gather_persist_s<true, false>(e, st, p, lpr, grid, smem);
+  return launch_gather_persist_s<false, false>(e, st, p, lpr, grid, smem);
 }
 
 template <bool DOT>
@@ -560,8 +564,18 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
 // Note: making the gather of query i+1 wait for the gather of query i (so that lanes overlap
 // only MLP/copy work with the HBM-bound gather) was measured slower on B200 than letting two
 // gathers share the chip (RMC1 16384 samples, 3 lanes: 60.5 vs 65.6 M inf/s).
-int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
+bool persistent_gather_ok(const drs_engine* e, bool dot) {
+  return e->gather_ctas_per_sm > 0 && !dot && !e->table_major && e->lpr > 0 &&
+         (int)e->owned.size() * (e->SB + 1) <= kPersistOffRegs * kSlsThreads &&
+         sls_persist_smem_bytes((int)e->owned.size(), e->SB, e->idx_cap, e->short_seg) <=
+             100 * 1024;
+}
+
+// pk != nullptr: coalesced requests (B = stacked rows); persistent_gather_ok() must hold
+int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot,
+                  const SlsPackets* pk = nullptr) {
   SlsLaunch p{};
+  if (pk) p.pk = *pk;
   p.tables = s.descs; p.T = (int)e->owned.size(); p.B = B; p.D = e->D;
   p.out = ln.G; p.ld_out = e->ld_G;
   p.SB = e->SB; p.idx_cap = e->idx_cap;
@@ -589,17 +603,15 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot) {
     }
   }
   if (p.T == 0) return DRS_OK;
-  int grid = ceil_div(B, e->SB);
+  int grid = pk ? pk->tile_off[pk->n] : ceil_div(B, e->SB);
   // persistent path: vectorised rows, no dot fusion, offsets fit the per-thread registers
-  if (e->gather_ctas_per_sm > 0 && !dot && !e->table_major && e->lpr > 0 &&
-      p.T * (e->SB + 1) <= kPersistOffRegs * kSlsThreads) {
+  if (persistent_gather_ok(e, dot)) {
     p.short_seg = e->short_seg ? 1 : 0;
     const size_t smem = sls_persist_smem_bytes(p.T, e->SB, e->idx_cap, e->short_seg);
-    if (smem <= 100 * 1024) {
-      const int cap = e->n_sm * e->gather_ctas_per_sm;
-      return launch_gather_persist(e, ln.stream, p, e->lpr, grid < cap ? grid : cap, smem);
-    }
+    const int cap = e->n_sm * e->gather_ctas_per_sm;
+    return launch_gather_persist(e, ln.stream, p, e->lpr, grid < cap ? grid : cap, smem);
   }
+  if (pk) return fail(DRS_ERR_STATE, "coalesced requests need the persistent gather");
   if (e->table_major && !dot) {
     p.tiles_per_table = grid;
     grid *= p.T;
@@ -710,7 +722,9 @@ int check_ready(drs_engine* e) {
 
 // B = samples of the whole query.  Single GPU: rows = B.  Sharded: this rank runs the dense
 // part on its slice [row0, row0 + rows) and gathers its tables for all B samples.
-int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
+// pk: coalesced requests — B stacked rows, dense rows already stacked in `dense_stacked`.
+int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
+                  const SlsPackets* pk = nullptr, const float* dense_stacked = nullptr) {
   const int D = e->D, T = e->T;
   int row0 = 0, rows = B;
   if (e->world > 1) {
@@ -722,7 +736,8 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
   }
   // dense rows of this rank inside s.dense
   const float* dense = s.dense ? s.dense + (int64_t)(row0 - s.dense_row0) * e->m_den : nullptr;
-  const int64_t dense_rows_left = s.dense_rows - (row0 - s.dense_row0);
+  int64_t dense_rows_left = s.dense_rows - (row0 - s.dense_row0);
+  if (pk) { dense = dense_stacked; dense_rows_left = e->spec.max_batch; }
   const int64_t cap = e->spec.max_batch;
   PROF_MARK(0);
   switch (e->spec.model_type) {
@@ -732,7 +747,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       else TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows, ln.R,
                        e->ld_R));
       PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, e->dot));
+      TRY(launch_gather(e, ln, s, B, e->dot, pk));
       PROF_MARK(2);
       TRY(exchange_after_gather(e, ln, rows));
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
@@ -746,7 +761,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
         e->launches += 1;
       }
       PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, false));
+      TRY(launch_gather(e, ln, s, B, false, pk));
       PROF_MARK(2);
       TRY(exchange_after_gather(e, ln, rows));
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
@@ -762,7 +777,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
         e->launches += 1;
       }
       PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, false));
+      TRY(launch_gather(e, ln, s, B, false, pk));
       PROF_MARK(2);
       TRY(exchange_after_gather(e, ln, rows));
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
@@ -787,7 +802,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       const int64_t ldp = (int64_t)T * D;
       const int N = e->n_steps, H = e->H;
       PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, false));
+      TRY(launch_gather(e, ln, s, B, false, pk));
       PROF_MARK(2);
       if (rows > 0) {
         k_dien_seq<<<ew_grid((int64_t)N * rows * D), 256, 0, ln.stream>>>(ln.P, ldp, ln.seq, rows,
@@ -834,7 +849,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       const int64_t ldp = (int64_t)T * D;
       const int ldf = D + e->top.layers.back().out;
       PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, false));
+      TRY(launch_gather(e, ln, s, B, false, pk));
       PROF_MARK(2);
       TRY(exchange_after_gather(e, ln, rows));
       if (rows > 0) {
@@ -851,7 +866,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B) {
       const int64_t ldp = (int64_t)T * D;
       const int nu = e->n_units;
       PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, false));
+      TRY(launch_gather(e, ln, s, B, false, pk));
       PROF_MARK(2);
       TRY(exchange_after_gather(e, ln, rows));
       if (rows > 0) {
@@ -1607,6 +1622,74 @@ int drs_submit_host(drs_engine* e, const float* dense, const void* const* idx, i
   Lane& ln = pick_lane(e);
   CU(cudaStreamSynchronize(ln.stream));      // the lane's input slot is reused
   TRY(enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out_pinned));
+  *ticket = make_ticket(e);
+  return DRS_OK;
+} DRS_CATCH
+
+// Coalesced serving: n queued requests -> ONE stacked query.  The dense rows are stacked by one
+// small kernel, K1 pools every request's segments into consecutive row ranges in one launch
+// (SlsPackets), and the MLPs run once over the stacked rows: per request 1 + 2/n launches
+// instead of 3, and one D2H copy for all of them.
+int drs_submit_many(drs_engine* e, int n, const int32_t* batch_ids, const int32_t* batch_sizes,
+                    float* out_pinned, int64_t* ticket) try {
+  CHECK_ARG(e && ticket && batch_ids && batch_sizes, "NULL argument");
+  CHECK_ARG(n >= 1 && n <= kMaxPackets, "n = %d requests out of range [1,%d]", n, kMaxPackets);
+  CHECK_ARG(e->world == 1, "coalesced serving runs on unsharded engines (replicas)");
+  CU(cudaSetDevice(e->device));
+  TRY(check_ready(e));
+  int64_t total = 0;
+  const InputSet* sets[kMaxPackets];
+  for (int k = 0; k < n; ++k) {
+    auto it = e->staged.find(batch_ids[k]);
+    if (it == e->staged.end()) return fail(DRS_ERR_STATE, "batch %d was not staged", batch_ids[k]);
+    CHECK_ARG(batch_sizes[k] >= 1 && batch_sizes[k] <= it->second.n,
+              "request %d: batch_size %d out of range [1,%d]", k, batch_sizes[k], it->second.n);
+    sets[k] = &it->second;
+    total += batch_sizes[k];
+  }
+  CHECK_ARG(total <= e->spec.max_batch, "%lld stacked samples exceed max_batch %d",
+            (long long)total, e->spec.max_batch);
+  Lane& ln = pick_lane(e);
+  const bool stack = n > 1 && e->spec.model_type != DRS_MODEL_DIEN &&   // DIEN's reshape mixes the
+                     persistent_gather_ok(e, e->dot);                   // samples of one query
+  if (!stack) {
+    // graphs that cannot be stacked: the requests run back to back on this lane, each copying its
+    // rows to its place in out_pinned (stream order keeps ln.out safe)
+    int64_t row = 0;
+    for (int k = 0; k < n; ++k) {
+      TRY(enqueue_graph(e, ln, *sets[k], batch_sizes[k]));
+      if (out_pinned)
+        CU(cudaMemcpyAsync(out_pinned + row * e->out_dim, ln.out,
+                           (size_t)batch_sizes[k] * e->out_dim * sizeof(float),
+                           cudaMemcpyDeviceToHost, ln.stream));
+      row += batch_sizes[k];
+    }
+    *ticket = make_ticket(e);
+    return DRS_OK;
+  }
+  SlsPackets pk{};
+  StackRows sr{};
+  pk.n = sr.n = n;
+  sr.ncols = e->m_den;
+  int row = 0, tile = 0;
+  for (int k = 0; k < n; ++k) {
+    pk.tile_off[k] = tile; pk.row_off[k] = row; pk.size[k] = batch_sizes[k];
+    pk.descs[k] = sets[k]->descs;
+    sr.row_off[k] = row; sr.src[k] = sets[k]->dense;
+    tile += ceil_div(batch_sizes[k], e->SB);
+    row += batch_sizes[k];
+  }
+  pk.tile_off[n] = tile;
+  sr.row_off[n] = row;
+  if (e->m_den > 0) {
+    k_stack_rows<<<ew_grid((int64_t)row * e->m_den / 4 + 1), 256, 0, ln.stream>>>(sr, ln.slot.dense);
+    CU(cudaGetLastError());
+    e->launches += 1;
+  }
+  TRY(enqueue_graph(e, ln, *sets[0], row, &pk, ln.slot.dense));
+  if (out_pinned)
+    CU(cudaMemcpyAsync(out_pinned, ln.out, (size_t)row * e->out_dim * sizeof(float),
+                       cudaMemcpyDeviceToHost, ln.stream));
   *ticket = make_ticket(e);
   return DRS_OK;
 } DRS_CATCH

@@ -7,6 +7,9 @@
 //   k_add_cols     Sum(e0, e1): NCF "MF" branch (ncf.py:303)
 //   k_din_concat   per behaviour table u: [e_u, e_ad, e_u + e_ad]  (din.py:263-273)
 //   k_sum_units    Sum over attention-unit outputs, in unit order (din.py:283)
+//   k_stack_rows   coalesced serving: the dense rows of several requests (each "the first
+//                  size_k rows of staged batch b_k", inferenceEngine.py:213) -> one stacked
+//                  [sum size_k, m_den] matrix, so that ONE MLP launch serves all of them
 #pragma once
 
 #include "common.cuh"
@@ -62,6 +65,25 @@ __global__ void k_sum_units(const float* __restrict__ units, int64_t unit_stride
     float acc = units[i];
     for (int u = 1; u < n_units; ++u) acc += units[(int64_t)u * unit_stride + i];
     dst[b * ldd + c] = acc;
+  }
+}
+
+constexpr int kStackMaxSrc = 32;
+struct StackRows {
+  int n;                                  // requests
+  int ncols;                              // floats per row
+  int row_off[kStackMaxSrc + 1];          // first stacked row of request k; row_off[n] = total rows
+  const float* src[kStackMaxSrc];         // [size_k, ncols] (row pitch = ncols)
+};
+
+__global__ void k_stack_rows(const StackRows p, float* __restrict__ dst) {
+  const int64_t n = (int64_t)p.row_off[p.n] * p.ncols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / p.ncols);
+    int k = 0;
+    while (k + 1 < p.n && row >= p.row_off[k + 1]) ++k;
+    dst[i] = __ldg(p.src[k] + (i - (int64_t)p.row_off[k] * p.ncols));
   }
 }
 

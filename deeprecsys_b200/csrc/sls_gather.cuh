@@ -46,6 +46,18 @@ struct SlsTableDesc {
   int32_t pad_;
 };
 
+// Coalesced serving (drs_submit_many): several queued requests, each "the first size_k samples of
+// staged batch b_k" (inferenceEngine.py:200-215), are pooled by ONE launch into consecutive row
+// ranges of the interaction buffer.  A tile never straddles two requests.
+constexpr int kMaxPackets = 32;
+struct SlsPackets {
+  int n;                               // 0: a single query (SlsLaunch::tables / B)
+  int tile_off[kMaxPackets + 1];       // first tile of request k; tile_off[n] = number of tiles
+  int row_off[kMaxPackets];            // first output row of request k
+  int size[kMaxPackets];               // samples of request k
+  const SlsTableDesc* descs[kMaxPackets];   // gather descriptors of request k's staged batch
+};
+
 struct SlsLaunch {
   const SlsTableDesc* tables;
   int T, B, D;
@@ -75,6 +87,7 @@ struct SlsLaunch {
   // short segments (avg length < 8: WnD / NCF / DIEN / DIN): the persistent kernel's SHORT
   // instantiation walks kSlsShort segments per lane group at once
   int short_seg;
+  SlsPackets pk;          // MULTI instantiation of the persistent kernel only
 };
 
 __host__ __device__ inline size_t sls_smem_bytes(int T, int SB, int idx_cap, int D, bool fuse_dot) {
@@ -361,7 +374,8 @@ __host__ __device__ inline size_t sls_persist_smem_bytes(int T, int SB, int idx_
 // SHORT: compile the multi-segment path for short segments (ids from global memory) instead of
 // the long-segment path — a separate instantiation so that its extra registers do not lower the
 // occupancy of the HBM-bound long-segment kernel.
-template <int LPR, bool SHORT>
+// MULTI: the tiles enumerate the requests of SlsLaunch::pk instead of one query.
+template <int LPR, bool SHORT, bool MULTI = false>
 __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);            // bar[0], bar[1]
@@ -373,24 +387,38 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
 
   const int tid = threadIdx.x;
   const int T = p.T;
-  const SlsTableDesc* __restrict__ tabs = p.tables;
-  const int ntiles = (p.B + p.SB - 1) / p.SB;
+  const int ntiles = MULTI ? p.pk.tile_off[p.pk.n] : (p.B + p.SB - 1) / p.SB;
   const bool use_smem_idx = p.idx_cap > 0;
   constexpr int L = LPR;
   const int group = tid / L, lane = tid - group * L;
   constexpr int ngroups = kSlsThreads / L;
 
+  // where a tile lives: descriptors of its request, first sample inside the request's staged
+  // batch, samples in the tile, first output row
+  struct TileLoc { const SlsTableDesc* tabs; int b0, sbe, row0; };
+  auto locate = [&](int tile) -> TileLoc {
+    if (!MULTI) {
+      const int b0 = tile * p.SB;
+      return TileLoc{p.tables, b0, min(p.SB, p.B - b0), b0};
+    }
+    int k = 0;
+    while (k + 1 < p.pk.n && tile >= p.pk.tile_off[k + 1]) ++k;
+    const int b0 = (tile - p.pk.tile_off[k]) * p.SB;
+    return TileLoc{p.pk.descs[k], b0, min(p.SB, p.pk.size[k] - b0), p.pk.row_off[k] + b0};
+  };
+
   // offsets of tile `tile` held by this thread (entries tid, tid + kSlsThreads)
   auto load_offs = [&](int tile, int32_t* regs) {
-    const int b0 = tile * p.SB;
-    const int sbe = min(p.SB, p.B - b0);
+    TileLoc loc{p.tables, 0, 0, 0};
+    if (tile < ntiles) loc = locate(tile);
+    const int b0 = loc.b0, sbe = loc.sbe;
 #pragma unroll
     for (int k = 0; k < kPersistOffRegs; ++k) {
       const int i = tid + k * kSlsThreads;
       regs[k] = 0;
       if (i < noff && tile < ntiles) {
         const int t = i / SB1, j = i - t * SB1;
-        if (j <= sbe) regs[k] = __ldg(tabs[t].off + b0 + j);
+        if (j <= sbe) regs[k] = __ldg(loc.tabs[t].off + b0 + j);
       }
     }
   };
@@ -402,8 +430,8 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
     }
   };
   auto issue_spans = [&](int tile, int buf) {      // index spans of `tile` -> sidx[buf] by TMA
-    const int b0 = tile * p.SB;
-    const int sbe = min(p.SB, p.B - b0);
+    const TileLoc loc = locate(tile);
+    const int sbe = loc.sbe;
     const int32_t* so = soff0 + (size_t)buf * noff;
     for (int t = tid; t < T; t += kSlsThreads) {
       const int beg = so[t * SB1], end = so[t * SB1 + sbe];
@@ -411,7 +439,7 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
       const int n = (end - a0 + 3) & ~3;
       if (n > 0 && n <= p.idx_cap) {
         mbar_arrive_expect_tx(&bar[buf], (uint32_t)n * 4u);
-        tma_load_1d(sidx0 + (size_t)buf * idx_words + (size_t)t * p.idx_cap, tabs[t].idx + a0,
+        tma_load_1d(sidx0 + (size_t)buf * idx_words + (size_t)t * p.idx_cap, loc.tabs[t].idx + a0,
                     (uint32_t)n * 4u, &bar[buf]);
       } else {
         mbar_arrive(&bar[buf]);
@@ -422,9 +450,11 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
   int tile = blockIdx.x;
   if (tile >= ntiles) return;
   // SHORT: a segment is a handful of rows, so even the 40-byte descriptor fetch from global
-  // memory would sit on its critical path -> keep the descriptors in shared memory
+  // memory would sit on its critical path -> keep the descriptors in shared memory (single
+  // query only: coalesced requests bring one descriptor set each)
+  const SlsTableDesc* __restrict__ tabs = p.tables;
   const SlsTableDesc* sdesc = tabs;
-  if (SHORT) {
+  if (SHORT && !MULTI) {
     size_t o = 32 + (2 * idx_words + 2 * (size_t)noff) * sizeof(int32_t);
     o = (o + 15) & ~size_t(15);
     SlsTableDesc* sd = reinterpret_cast<SlsTableDesc*>(smem_raw + o);
@@ -456,8 +486,10 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
     if (use_smem_idx && next_tile < ntiles) issue_spans(next_tile, nxt);
     if (use_smem_idx) mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
 
-    const int b0 = tile * p.SB;
-    const int sbe = min(p.SB, p.B - b0);
+    const TileLoc loc = locate(tile);
+    const int b0 = loc.row0;                       // first OUTPUT row of the tile
+    const int sbe = loc.sbe;
+    if (MULTI) { tabs = loc.tabs; sdesc = loc.tabs; }
     const int32_t* so = soff0 + (size_t)cur * noff;
     const int32_t* si = sidx0 + (size_t)cur * idx_words;
     const int nseg = sbe * T;

@@ -210,6 +210,20 @@ class AccelEngine(object):
                                             int(batch_size), out_ptr, C.byref(t)))
         return t.value
 
+    MAX_COALESCE = 32
+
+    def submit_many(self, batch_ids, batch_sizes, out_ptr=None):
+        """Coalesced serve of up to 32 queued requests (request k = first ``batch_sizes[k]``
+        samples of staged batch ``batch_ids[k]``) as ONE stacked query: one gather launch, one
+        pass of the MLPs, one D2H copy.  Row r of request k lands at row
+        ``sum(batch_sizes[:k]) + r`` of the output.  Returns a ticket for ``wait``."""
+        n = len(batch_ids)
+        ids = (C.c_int32 * n)(*batch_ids)
+        sizes = (C.c_int32 * n)(*batch_sizes)
+        t = C.c_int64()
+        _lib.check(self.lib.drs_submit_many(self._handle, n, ids, sizes, out_ptr, C.byref(t)))
+        return t.value
+
     def wait(self, ticket):
         _lib.check(self.lib.drs_wait(self._handle, int(ticket)))
 

@@ -133,6 +133,8 @@ class SystemHarness(object):
                                 args=(args, self.accel_q, 0, self.resp_q, self.ready_q))
         self.proc.daemon = True
         self.proc.start()
+        from deeprecsys_b200.utils.fastqueue import FrameReader
+        self.resp_reader = FrameReader(self.resp_q)
         self.ready_q.get()                                    # loadGenerator.py:76-78
 
     def run(self, n_queries, arrival_ms, seed=0, warmup_queries=20, timeout_s=300.0):
@@ -146,16 +148,21 @@ class SystemHarness(object):
         gen.start()
         got = []
         deadline = time.time() + timeout_s
-        while len(got) < n_total and time.time() < deadline:
-            try:
-                r = self.resp_q.get(timeout=1.0)
-            except _queue.Empty:
+        # the collector must keep up with ~100 k responses/s: batched pipe reads (same protocol
+        # as resp_q.get(), utils/fastqueue.py); latencies come from the stamps inside the
+        # responses, not from when the collector sees them
+        ended = False
+        while len(got) < n_total and time.time() < deadline and not ended:
+            batch = self.resp_reader.drain(block=True, timeout=1.0)
+            if not batch:
                 if not self.proc.is_alive():
                     break
                 continue
-            if r is None:
-                break
-            got.append(r)
+            for r in batch:
+                if r is None:
+                    ended = True
+                    break
+                got.append(r)
         try:
             t_first, _ = report_q.get(timeout=10.0)
         except _queue.Empty:
@@ -184,13 +191,12 @@ class SystemHarness(object):
         import queue as _queue
         self.accel_q.put(None)
         deadline = time.time() + 120
-        while time.time() < deadline:
-            try:
-                if self.resp_q.get(timeout=1.0) is None:
-                    break
-            except _queue.Empty:
-                if not self.proc.is_alive():
-                    break
+        ended = False
+        while time.time() < deadline and not ended:
+            batch = self.resp_reader.drain(block=True, timeout=1.0)
+            if not batch and not self.proc.is_alive():
+                break
+            ended = any(r is None for r in batch)
         self.proc.join(timeout=60)
         if self.proc.is_alive():
             self.proc.terminate()
@@ -220,7 +226,12 @@ def sweep(args, rates_ms, n_queries, target_p99_ms=None, ring=False):
     ok = [r for r in rows if r["p99_ms"] <= target and r["failed"] == 0]
     best = max(ok, key=lambda r: r["inferences_per_s"]) if ok else None
     return {"target_p99_ms": target, "runs": rows, "best": best,
-            "inputs": "shared-memory ring (TensorServiceRequest)" if ring else "batch_id"}
+            "inputs": "shared-memory ring (TensorServiceRequest)" if ring else "batch_id",
+            "engine": {"accel_coalesce": int(getattr(args, "accel_coalesce", 1)),
+                       "accel_stack_rows": int(getattr(args, "accel_stack_rows", 0)),
+                       "accel_responder": int(getattr(args, "accel_responder", 0)),
+                       "accel_lanes": int(getattr(args, "accel_lanes", 0)),
+                       "accel_gpus": int(getattr(args, "accel_gpus", 1))}}
 
 
 def main(argv=None):

@@ -122,6 +122,12 @@ ACCEL_FLAGS = (
     ("accel_upload_inputs", _T, False),  # H2D per query instead of pre-staged batches
     ("accel_gpus", int, 1),              # GPUs behind the single accel slot (replicas; sibling
                                          # processes share accelRequestQueue / responseQueue)
+    ("accel_coalesce", int, 16),         # requests already waiting on the accel queue that one
+                                         # launch may serve together (1 = one launch per request)
+    ("accel_stack_rows", int, 4096),     # most samples one coalesced launch stacks
+    ("accel_lanes", int, 0),             # queries in flight on the GPU (0 = library default, 2)
+    ("accel_responder", int, 1),         # 1: ServiceResponses are built and sent by a helper
+                                         # process fed through a shared-memory ring
     ("data_trace_sort_lookups", _T, False),  # --data_generation synthetic: sort the ids inside
                                          # every lookup (the random generator's np.unique does)
 )

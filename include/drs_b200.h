@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRS_ABI_VERSION 5
+#define DRS_ABI_VERSION 6
 
 /* status codes */
 enum {
@@ -179,6 +179,15 @@ int drs_submit_staged(drs_engine* e, int batch_id, int batch_size, float* out_pi
 int drs_submit_host(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,
                     const int32_t* const* lengths, int batch_size, float* out_pinned,
                     int64_t* ticket);
+/* Coalesced serving ("multi-query batching on the accel queue"): n <= 32
+ * queued requests, request k = "the first batch_sizes[k] samples of staged batch batch_ids[k]"
+ * (inferenceEngine.py:200-215), are served as ONE stacked query: one K1 launch pools all of
+ * them into consecutive row ranges and the MLPs run once over sum(batch_sizes) <= max_batch
+ * rows.  Row r of request k lands at out_pinned[(sum_{j<k} batch_sizes[j] + r) * out_dim].
+ * Results are the same values as n separate drs_submit_staged calls (pooled vectors
+ * bit-identical; every sample's MLP arithmetic is independent of its row position). */
+int drs_submit_many(drs_engine* e, int n, const int32_t* batch_ids, const int32_t* batch_sizes,
+                    float* out_pinned, int64_t* ticket);
 int drs_wait(drs_engine* e, int64_t ticket);
 int drs_lane_count(const drs_engine* e, int* n_lanes);
 

@@ -210,6 +210,57 @@ def test_pipelined_siblings_never_sit_on_an_in_flight_packet():
     assert not p.is_alive()
 
 
+class CoalescingBackend(PipelinedBackend):
+    """Backend with drs_submit_many semantics: several queued requests -> one stacked launch."""
+    depth = 2
+    stack_rows = 150
+    can_coalesce = True
+
+    def submit_many(self, batch_ids, sizes):
+        with open(os.path.join(os.environ["DRS_TEST_PID_DIR"], "groups"), "a") as f:
+            f.write(" ".join(str(n) for n in sizes) + "\n")
+        return ("many", list(batch_ids), list(sizes))
+
+    def complete(self, handle):
+        if handle[0] != "many":
+            return PipelinedBackend.complete(self, handle)
+        time.sleep(0.003)                          # a launch takes a while: requests pile up
+        if 3 in handle[1]:
+            raise RuntimeError("injected failure")
+        return np.full((sum(handle[2]), 1), 0.5, np.float32)
+
+
+@pytest.mark.parametrize("responder", [1, 0])
+def test_coalesced_serving_answers_every_request_exactly_once(tmp_path, monkeypatch, responder):
+    """--accel_coalesce: requests that are already waiting are served by one launch; every request
+    still gets its own ServiceResponse with its own fields (through the responder helper process
+    or in-process), a failed launch answers all of its requests with 0, the final sentinel comes
+    after the last response."""
+    monkeypatch.setenv("DRS_TEST_PID_DIR", str(tmp_path))
+    reqs = [_req(3 if i in (40, 41, 150) else i % 3, 10 + i % 50, epoch=i) for i in range(240)]
+    reqs[17].exp_packet = True
+    reqs[18].sub_id, reqs[18].total_sub_batches = 2, 5
+    out = _run_engine(CoalescingBackend, reqs, extra=["--accel_coalesce", "8",
+                                                      "--accel_responder", str(responder)])
+    assert len(out) == len(reqs)
+    key = lambda r: (r.epoch, r.batch_id, r.batch_size, r.sub_id, r.total_sub_batches,
+                     r.exp_packet, r.arrival_time)
+    assert sorted(map(key, out)) == sorted(map(key, reqs))
+    assert all(r.consumer_id == 7 for r in out)
+    assert all(r.queue_start_time <= r.queue_end_time == r.inference_end_time for r in out)
+    groups = [[int(x) for x in line.split()]
+              for line in open(str(tmp_path / "groups")).read().splitlines()]
+    assert groups and max(len(g) for g in groups) > 1            # requests really were stacked
+    assert all(2 <= len(g) <= 8 and sum(g) <= 150 for g in groups)
+    # a request in a failed launch (one that contained batch_id 3) is answered with 0, every
+    # other one with its size
+    zero = [r for r in out if r.out_batch_size == 0]
+    assert zero and all(r.out_batch_size in (0, r.batch_size) for r in out)
+    assert any(r.batch_id == 3 for r in zero)
+    assert any(r.batch_id == 3 and r.out_batch_size == 0 for r in out)
+    assert len(zero) <= 3 * 8
+
+
 def test_engine_without_queue_exits_like_the_reference():
     args = cli(SMALL_SYSTEM)
     with pytest.raises(SystemExit):
