@@ -69,7 +69,7 @@ class AccelBackend(object):
             cap = max(cap, int(getattr(args, "accel_stack_rows", 0) or 0))
         self.engine = AccelEngine(args=args, device=int(getattr(args, "accel_device", 0)),
                                   max_batch=cap, lanes=int(getattr(args, "accel_lanes", 0) or 0),
-                                  max_lookups_per_table=int(args.max_mini_batch_size)
+                                  max_lookups_per_table=cap
                                   * max(1, int(args.num_indices_per_lookup)))
         self.stack_rows = cap
         self.engine.create()                               # tables -> MLPs, reference draw order

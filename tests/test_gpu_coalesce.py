@@ -22,8 +22,7 @@ REQUESTS = [(0, 13), (1, 64), (0, 1), (1, 40), (0, 64), (1, 7)]
 def test_coalesced_requests_equal_single_requests_and_the_oracle(name, precision):
     c = make_case(name, num_batches=2, max_batch=64)
     total = sum(n for _, n in REQUESTS)
-    with AccelEngine(args=c.args, max_batch=256, precision=precision,
-                     max_lookups_per_table=64 * max(1, c.spec.L)) as eng:
+    with AccelEngine(args=c.args, max_batch=256, precision=precision) as eng:
         eng.load_parameters(c.tables, c.fcs)
         for j in range(2):
             dense, ids, lengths = request(c, j, 64)
@@ -57,7 +56,7 @@ def test_coalesced_requests_equal_single_requests_and_the_oracle(name, precision
 
 def test_coalesced_requests_are_validated():
     c = make_case("dlrm_cat", num_batches=1, max_batch=64)
-    with AccelEngine(args=c.args, max_batch=100, max_lookups_per_table=64 * c.spec.L) as eng:
+    with AccelEngine(args=c.args, max_batch=100) as eng:
         eng.load_parameters(c.tables, c.fcs)
         dense, ids, lengths = request(c, 0, 64)
         eng.stage_batch(0, dense, ids, lengths)
