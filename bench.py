@@ -609,6 +609,8 @@ class Workload(object):
                "note": "per step H2D -> kernels -> D2H, steps pipelined over the engine lanes, "
                        "wall clock incl. final sync, max over ranks"}
         if int64_too:
+            e2e["packed_ids"] = self.measure_e2e_packed(steps, h)
+        if int64_too:
             # the same step with int64 ids, the dtype the reference's run_queues receives from
             # np.array(list) (the Cast to int32 then runs on the GPU): twice the id bytes over PCIe
             h64, _k = pinned_empty((T, B * L), np.int64)
@@ -628,6 +630,44 @@ class Workload(object):
             e2e["int64_ids"] = {"value": env.world * B * n64 / dt64, "unit": UNIT, "steps": n64,
                                 "h2d_bytes_per_step": B * (T * L * 8 + T * 4 + spec.m_den * 4)}
         return e2e
+
+    def measure_e2e_packed(self, steps, h):
+        """The same step with the ids in the packed wire format (ceil(log2(rows)) bits per id,
+        drs_pack_ids): fewer bytes over PCIe, widened to int32 on the GPU.  Packing is the
+        CLIENT's job (as producing int32 instead of int64 is today) and is timed separately."""
+        from deeprecsys_b200.engine import id_bits, pack_ids, pinned_empty
+        from deeprecsys_b200 import _lib
+        env, eng, spec, B = self.env, self.eng, self.spec, self.B
+        T, L = spec.T, spec.L
+        bits = [id_bits(r) for r in spec.table_rows]
+        lib = _lib.load()
+        words = [int(lib.drs_packed_words(B * L, b)) for b in bits]
+        bufs, keep = [], []
+        t0 = time.perf_counter()
+        for t in range(T):
+            arr, owner = pinned_empty((words[t],), np.uint32)
+            pack_ids(h["idx"][t], bits[t], out=arr)
+            bufs.append(arr); keep.append(owner)
+        pack_s = time.perf_counter() - t0
+        pptrs = (C.c_void_p * T)(*[b.ctypes.data for b in bufs])
+        cbits = (C.c_int32 * T)(*bits)
+        for _ in range(3):
+            eng.enqueue_host_packed(h["den_ptr"], pptrs, cbits, h["len_ptrs"], B, h["out_ptr"])
+        eng.sync()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.enqueue_host_packed(h["den_ptr"], pptrs, cbits, h["len_ptrs"], B, h["out_ptr"])
+        eng.sync()
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        return {"value": env.world * B * steps / dt, "unit": UNIT, "steps": steps,
+                "bits_per_id": bits[0] if len(set(bits)) == 1 else bits,
+                "h2d_bytes_per_step": int(sum(words) * 4 + B * (T * 4 + spec.m_den * 4)),
+                "client_pack_ns_per_id_one_core": 1e9 * pack_s / max(1, T * B * L),
+                "note": "ids pre-packed by the client (pack cost reported, not inside the "
+                        "timed region: at ~%.1f ns per id a host core packs fewer ids than PCIe "
+                        "moves, so packing on the serving host would not pay)"
+                        % (1e9 * pack_s / max(1, T * B * L))}
 
     def measure_latency(self, h, q=1024, n=220):
         """Per-query wall latency at the reference's largest query size, host path.  The first

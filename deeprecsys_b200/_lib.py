@@ -76,6 +76,10 @@ _SIGNATURES = {
     "drs_enqueue_host": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int,
                                    C.c_void_p]),
     "drs_sync": (C.c_int, [C.c_void_p]),
+    "drs_packed_words": (C.c_int64, [C.c_int64, C.c_int]),
+    "drs_pack_ids": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "drs_enqueue_host_packed": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.POINTER(C.c_int32), _PP,
+                                          C.c_int, C.c_void_p]),
     "drs_submit_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                     C.POINTER(C.c_int64)]),
     "drs_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.c_int, _PP, C.c_int, C.c_void_p,

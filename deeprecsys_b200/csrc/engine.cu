@@ -950,9 +950,10 @@ Lane& pick_lane(drs_engine* e) {
 
 // upload one query into an InputSet (host -> device on `stream`).  Sharded: ids are uploaded
 // only for owned tables (lengths and dense rows for all: they are small).
+// pack_bits != nullptr: idx[t] is a packed stream of pack_bits[t]-bit ids (drs_pack_ids)
 int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* dense,
                   const void* const* idx, int idx_is_i64, const int32_t* const* lengths, int B,
-                  std::vector<int64_t>* n_idx_out) {
+                  std::vector<int64_t>* n_idx_out, const int32_t* pack_bits = nullptr) {
   const int T = e->T;
   CHECK_ARG(B >= 0 && B <= s.n, "batch_size %d exceeds capacity %d", B, s.n);
   CHECK_ARG(idx && lengths, "idx/lengths pointer arrays must not be NULL");
@@ -994,7 +995,17 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
   }
   const size_t isz = idx_is_i64 ? sizeof(int64_t) : sizeof(int32_t);
   // ids: equal counts + equal host stride + equal device stride -> one 2-D copy
-  bool idx_strided = T > 1 && !idx_is_i64 && (e->world == 1 || row);
+  if (pack_bits) {
+    CHECK_ARG(s.idx64 != nullptr, "packed ids need the host-path input slot");
+    for (int t = 0; t < T; ++t) {
+      int need = 1;
+      while (need < 31 && (int64_t(1) << need) < e->table_rows[t]) ++need;
+      CHECK_ARG(pack_bits[t] >= need && pack_bits[t] <= 31,
+                "table %d: %d-bit ids cannot address %lld rows (need %d..31 bits)", t,
+                pack_bits[t], (long long)e->table_rows[t], need);
+    }
+  }
+  bool idx_strided = T > 1 && !idx_is_i64 && !pack_bits && (e->world == 1 || row);
   const ptrdiff_t istride = T > 1 ? (const char*)idx[1] - (const char*)idx[0] : 0;
   const int64_t dstride = T > 1 ? s.idx_pos[1] - s.idx_pos[0] : 0;
   for (int t = 1; t < T && idx_strided; ++t)
@@ -1007,7 +1018,17 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
   } else {
     for (int t = 0; t < T; ++t) {
       if (n_idx[t] == 0 || !owns(e, t)) continue;
-      if (idx_is_i64) {
+      if (pack_bits) {
+        // packed words land in the (8 bytes per id) scratch, one kernel widens them to int32
+        const int64_t words = packed_words(n_idx[t], pack_bits[t]);
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(s.idx64 + s.idx_pos[t]);
+        CU(cudaMemcpyAsync(scratch, idx[t], (size_t)words * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice, stream));
+        k_unpack_ids<<<ew_grid(n_idx[t]), 256, 0, stream>>>(scratch, pack_bits[t], n_idx[t],
+                                                            dst_idx + s.idx_pos[t]);
+        CU(cudaGetLastError());
+        e->launches += 1;
+      } else if (idx_is_i64) {
         CU(cudaMemcpyAsync(s.idx64 + s.idx_pos[t], idx[t], (size_t)n_idx[t] * sizeof(int64_t),
                            cudaMemcpyHostToDevice, stream));
         k_cast_i64_i32<<<ew_grid(n_idx[t]), 256, 0, stream>>>(s.idx64 + s.idx_pos[t],
@@ -1553,7 +1574,7 @@ int drs_infer_staged(drs_engine* e, int batch_id, int batch_size, float* out, dr
 
 static int enqueue_host_on(drs_engine* e, Lane& ln, const float* dense, const void* const* idx,
                            int idx_is_i64, const int32_t* const* lengths, int batch_size,
-                           float* out_pinned) {
+                           float* out_pinned, const int32_t* pack_bits = nullptr) {
   const int64_t cap = (int64_t)e->spec.max_batch * e->world;
   CHECK_ARG(batch_size >= 1 && batch_size <= cap && batch_size <= ln.slot.n,
             "batch_size %d out of range [1,%lld]", batch_size, (long long)cap);
@@ -1561,7 +1582,8 @@ static int enqueue_host_on(drs_engine* e, Lane& ln, const float* dense, const vo
   TRY(check_ready(e));
   std::vector<int64_t> n_idx;
   CU(cudaEventRecord(ln.ev[0], ln.stream));
-  TRY(upload_inputs(e, ln.slot, ln.stream, dense, idx, idx_is_i64, lengths, batch_size, &n_idx));
+  TRY(upload_inputs(e, ln.slot, ln.stream, dense, idx, idx_is_i64, lengths, batch_size, &n_idx,
+                    pack_bits));
   CU(cudaEventRecord(ln.ev[1], ln.stream));
   TRY(launch_scan(e, ln.stream, ln.slot, batch_size, ln.d_err));
   TRY(enqueue_graph(e, ln, ln.slot, batch_size));
@@ -1580,6 +1602,38 @@ int drs_enqueue_host(drs_engine* e, const float* dense, const void* const* idx, 
   // the lane's input slot is reused: the previous query on this lane must have been consumed
   CU(cudaStreamSynchronize(ln.stream));
   return enqueue_host_on(e, ln, dense, idx, idx_is_i64, lengths, batch_size, out_pinned);
+} DRS_CATCH
+
+int64_t drs_packed_words(int64_t n_ids, int bits) { return packed_words(n_ids, bits); }
+
+int drs_pack_ids(const int32_t* ids, int64_t n_ids, int bits, uint32_t* out) try {
+  CHECK_ARG(ids && out && n_ids >= 0, "bad arguments");
+  CHECK_ARG(bits >= 1 && bits <= 31, "bits must be in [1,31]");
+  const int64_t words = packed_words(n_ids, bits);
+  const uint32_t limit = bits == 31 ? 0x7fffffffu : ((1u << bits) - 1u);
+  uint64_t acc = 0;
+  int fill = 0;
+  int64_t w = 0;
+  for (int64_t i = 0; i < n_ids; ++i) {
+    const uint32_t v = (uint32_t)ids[i];
+    if (v > limit) return fail(DRS_ERR_INDEX, "id %d at position %lld does not fit %d bits",
+                               ids[i], (long long)i, bits);
+    acc |= (uint64_t)v << fill;
+    fill += bits;
+    if (fill >= 32) { out[w++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+  }
+  while (w < words) { out[w++] = (uint32_t)acc; acc >>= 32; }      // tail + the pad word
+  return DRS_OK;
+} DRS_CATCH
+
+int drs_enqueue_host_packed(drs_engine* e, const float* dense, const uint32_t* const* packed,
+                            const int32_t* bits, const int32_t* const* lengths, int batch_size,
+                            float* out_pinned) try {
+  CHECK_ARG(e && packed && bits, "NULL argument");
+  Lane& ln = pick_lane(e);
+  CU(cudaStreamSynchronize(ln.stream));      // the lane's input slot is reused
+  return enqueue_host_on(e, ln, dense, reinterpret_cast<const void* const*>(packed), 0, lengths,
+                         batch_size, out_pinned, bits);
 } DRS_CATCH
 
 int drs_infer(drs_engine* e, const float* dense, const void* const* idx, int idx_is_i64,

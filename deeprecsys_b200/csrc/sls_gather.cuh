@@ -562,15 +562,21 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
 
 // lengths -> offsets (exclusive prefix sum), one CTA per table; also checks
 // Caffe2's enforce  sum(lengths) == len(indices)  when n_idx >= 0.
-// Integer-exact by construction.
+// Integer-exact by construction (int32 adds in any grouping are associative).
 struct ScanTableDesc {
   const int32_t* lengths;   // [B]
   int32_t* off;             // [B+1]
   int64_t n_idx;            // expected total, or -1
 };
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 16;                       // lengths per thread and pass
+constexpr int kScanChunk = kScanThreads * kScanItems;
 
+// One CTA per table, 16,384 lengths per pass: every thread scans 16 consecutive lengths in
+// registers, the 1,024 thread totals are scanned with two levels of warp shuffles, and each
+// thread adds its prefix while storing.  B = 16,384 is ONE pass (a few microseconds) instead of
+// 64 dependent 256-wide block scans.
 __global__ void __launch_bounds__(kScanThreads) k_lengths_to_offsets(const ScanTableDesc* tabs,
                                                                      int B, int* err_flag) {
   __shared__ int32_t warp_sums[kScanThreads / kWarp];
@@ -579,24 +585,46 @@ __global__ void __launch_bounds__(kScanThreads) k_lengths_to_offsets(const ScanT
   const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp;
   if (tid == 0) { carry_s = 0; td.off[0] = 0; }
   __syncthreads();
-  for (int base = 0; base < B; base += kScanThreads) {
-    const int i = base + tid;
-    int32_t v = (i < B) ? td.lengths[i] : 0;
-    if (v < 0) { *err_flag = 1; v = 0; }
-    int32_t x = v;  // inclusive warp scan
+  for (int base = 0; base < B; base += kScanChunk) {
+    const int i0 = base + tid * kScanItems;
+    int32_t v[kScanItems];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      int32_t x = (i0 + k < B) ? __ldg(td.lengths + i0 + k) : 0;
+      if (x < 0) { bad = true; x = 0; }
+      v[k] = x;
+    }
+    if (bad) *err_flag = 1;
+#pragma unroll
+    for (int k = 1; k < kScanItems; ++k) v[k] += v[k - 1];      // inclusive, thread-local
+    const int32_t total = v[kScanItems - 1];
+    int32_t x = total;                                          // inclusive scan of the thread totals
 #pragma unroll
     for (int d = 1; d < kWarp; d <<= 1) {
-      int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
       if (lane >= d) x += y;
     }
     if (lane == kWarp - 1) warp_sums[warp] = x;
     __syncthreads();
-    int32_t wprefix = 0;
-    for (int w = 0; w < warp; ++w) wprefix += warp_sums[w];
-    const int32_t carry = carry_s;
-    if (i < B) td.off[i + 1] = carry + wprefix + x;
+    if (warp == 0) {                                            // 32 warp totals -> exclusive prefixes
+      const int32_t w = warp_sums[lane];
+      int32_t z = w;
+#pragma unroll
+      for (int d = 1; d < kWarp; d <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, z, d);
+        if (lane >= d) z += y;
+      }
+      warp_sums[lane] = z - w;
+    }
     __syncthreads();
-    if (tid == kScanThreads - 1) carry_s = carry + wprefix + x;
+    const int32_t carry = carry_s;
+    const int32_t prefix = carry + warp_sums[warp] + (x - total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (i0 + k < B) td.off[i0 + k + 1] = prefix + v[k];
+    __syncthreads();
+    if (tid == kScanThreads - 1) carry_s = prefix + total;
     __syncthreads();
   }
   if (tid == 0 && td.n_idx >= 0 && (int64_t)carry_s != td.n_idx) *err_flag = 1;
@@ -608,6 +636,24 @@ __global__ void k_cast_i64_i32(const int64_t* __restrict__ src, int32_t* __restr
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = (int32_t)src[i];
+}
+
+// Packed id wire format (drs_pack_ids): id i occupies bits [i*bits, (i+1)*bits) of a
+// little-endian uint32 stream; one pad word follows so that a 64-bit window is always readable.
+__host__ __device__ inline int64_t packed_words(int64_t n_ids, int bits) {
+  return (n_ids * bits + 31) / 32 + 1;
+}
+
+__global__ void k_unpack_ids(const uint32_t* __restrict__ packed, int bits, int64_t n,
+                             int32_t* __restrict__ dst) {
+  const uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bit = i * bits;
+    const int64_t w = bit >> 5;
+    const uint64_t win = (uint64_t)__ldg(packed + w) | ((uint64_t)__ldg(packed + w + 1) << 32);
+    dst[i] = (int32_t)((uint32_t)(win >> (bit & 31)) & mask);
+  }
 }
 
 }  // namespace drs

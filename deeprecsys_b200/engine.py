@@ -195,6 +195,12 @@ class AccelEngine(object):
         _lib.check(self.lib.drs_enqueue_host(self._handle, dense_ptr, ids_ptrs, is64, len_ptrs,
                                              int(batch_size), out_ptr))
 
+    def enqueue_host_packed(self, dense_ptr, packed_ptrs, bits, len_ptrs, batch_size, out_ptr):
+        """``enqueue_host`` with ids in the packed wire format (``pack_ids``): ``bits`` is a
+        ctypes int32 array, one width per table."""
+        _lib.check(self.lib.drs_enqueue_host_packed(self._handle, dense_ptr, packed_ptrs, bits,
+                                                    len_ptrs, int(batch_size), out_ptr))
+
     def submit_staged(self, batch_id, batch_size, out_ptr=None):
         """Asynchronous serve of a staged batch; returns a ticket for ``wait``."""
         t = C.c_int64()
@@ -351,3 +357,22 @@ def pinned_empty(shape, dtype):
     buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr, p
+
+
+def id_bits(n_rows):
+    """Bits an id of an ``n_rows``-row table needs in the packed wire format."""
+    return max(1, int(n_rows - 1).bit_length())
+
+
+def pack_ids(ids, bits, out=None):
+    """int32 ids -> packed uint32 stream (``drs_pack_ids``).  ``out``: optional preallocated
+    (pinned) uint32 array of at least ``drs_packed_words(len(ids), bits)`` words."""
+    lib = _lib.load()
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    words = int(lib.drs_packed_words(ids.shape[0], int(bits)))
+    if out is None:
+        out = np.empty(words, dtype=np.uint32)
+    elif out.shape[0] < words or out.dtype != np.uint32:
+        raise ValueError("out must hold %d uint32 words" % words)
+    _lib.check(lib.drs_pack_ids(_ptr(ids), ids.shape[0], int(bits), _ptr(out)))
+    return out[:words]

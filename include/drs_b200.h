@@ -170,6 +170,19 @@ int drs_enqueue_host(drs_engine* e, const float* dense, const void* const* idx, 
                      const int32_t* const* lengths, int batch_size, float* out_pinned);
 int drs_sync(drs_engine* e);
 
+/* Packed ids (opt-in wire format for the upload path).  The ids of an n-row table need
+ * ceil(log2(n)) bits, not 32: RMC1's 4 M-row tables -> 22 bits, 31 % fewer bytes over PCIe, which
+ * is what bounds the upload path (SURVEY hard part 2).  drs_pack_ids writes id i into bits
+ * [i*bits, (i+1)*bits) of a little-endian uint32 stream of drs_packed_words(n, bits) words (the
+ * client's job, like producing int32 instead of int64 today); drs_enqueue_host_packed takes one
+ * such stream per table (bits[t] >= ceil(log2(rows[t])), <= 31) and widens them on the GPU to
+ * the int32 ids the gather reads — same Cast-to-int32 semantics as dlrm_s_caffe2.py:308. */
+int64_t drs_packed_words(int64_t n_ids, int bits);
+int drs_pack_ids(const int32_t* ids, int64_t n_ids, int bits, uint32_t* out);
+int drs_enqueue_host_packed(drs_engine* e, const float* dense, const uint32_t* const* packed,
+                            const int32_t* bits, const int32_t* const* lengths, int batch_size,
+                            float* out_pinned);
+
 /* Submit / wait pair for pipelined serving: up to drs_lane_count() queries may be in flight
  * (the copy and MLP kernels of one overlap the gather of the next).  out_pinned (nullable) must
  * be pinned host memory and stay valid until drs_wait(ticket) returns; drs_wait reports the

@@ -70,6 +70,10 @@ class FakeAccelEngine(object):
         assert 1 <= int(batch_size) <= self.max_batch
         self.launches += 4
 
+    def enqueue_host_packed(self, dense_ptr, packed_ptrs, bits, len_ptrs, batch_size, out_ptr):
+        assert 1 <= int(batch_size) <= self.max_batch
+        self.launches += 4 + self.spec.T
+
     def sync(self):
         pass
 
