@@ -32,6 +32,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -154,8 +155,8 @@ struct Lane {
   float* rnn_pre = nullptr;               // DIEN: i2h term of all steps [N*cap, H]
   float* rnn_h0 = nullptr;                // DIEN: hidden states of cell 0 [N*cap, H]
   float* out = nullptr;
-  int* d_err = nullptr;
-  int* h_err = nullptr;           // pinned
+  int* d_err = nullptr;           // device view of h_err (zero-copy: kernels raise the flag in
+  int* h_err = nullptr;           // mapped pinned host memory, no D2H copy per query)
   const InputSet* last_inputs = nullptr;
   int last_B = 0, last_rows = 0;
   uint32_t epoch = 0;             // sharded exchange epoch on this lane
@@ -188,6 +189,15 @@ struct drs_engine {
 
   int64_t launches = 0;
   int64_t hbm_bytes = 0;
+  bool ready = false;         // check_ready() passed since the last parameter change
+
+  // CUDA graphs of the staged single-query step, keyed by (lane, batch id, batch size): the
+  // step is 3-4 small launches, so at small batch sizes the CPU launch cost (not the GPU) bounds
+  // the rate; a replay is one cudaGraphLaunch.  Captured on first use, bounded LRU-less cache.
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int rows = 0; };
+  std::map<std::tuple<int, int, int>, StepGraph> graphs;
+  bool use_graphs = true;
+  int64_t graph_replays = 0;
   int64_t submit_seq = 0;
 
   // options (drs_set_option)
@@ -235,6 +245,12 @@ int dev_alloc_t(drs_engine* e, T** p, size_t count) {
 }
 
 cudaStream_t s0(drs_engine* e) { return e->lanes[0].stream; }
+
+void drop_graphs(drs_engine* e) {
+  for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+}
 
 int sync_all(drs_engine* e) {
   for (int i = 0; i < e->n_lanes; ++i) CU(cudaStreamSynchronize(e->lanes[i].stream));
@@ -701,6 +717,7 @@ int exchange_after_gather(drs_engine* e, Lane& ln, int rows) {
 
 // ------------------------------------------------------------ model graphs
 int check_ready(drs_engine* e) {
+  if (e->ready) return DRS_OK;               // cleared by every parameter load / shard connect
   for (int t = 0; t < e->T; ++t)
     if (owns(e, t) && !e->table_loaded[t])
       return fail(DRS_ERR_STATE, "embedding table %d not loaded", t);
@@ -710,6 +727,7 @@ int check_ready(drs_engine* e) {
   if (!e->task.all_loaded()) return fail(DRS_ERR_STATE, "task-head MLP weights not loaded");
   if (!e->rnn[0].all_loaded() || !e->rnn[1].all_loaded())
     return fail(DRS_ERR_STATE, "recurrent cell weights not loaded");
+  e->ready = true;
   return DRS_OK;
 }
 
@@ -907,7 +925,6 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
   PROF_MARK(3);
   if (e->prof_on && e->prof_n < e->prof_cap) e->prof_n += 1;
   if (e->world > 1) TRY(shard_signal(e, ln, 1, ln.epoch));   // my buffer may be overwritten
-  CU(cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
   ln.last_inputs = &s;
   ln.last_B = B;
   ln.last_rows = rows;
@@ -920,8 +937,6 @@ int finish_lane(drs_engine* e, Lane& ln) {
   if (*ln.h_err) {
     const int what = *ln.h_err;
     *ln.h_err = 0;
-    cudaMemsetAsync(ln.d_err, 0, sizeof(int), ln.stream);
-    cudaStreamSynchronize(ln.stream);
     if (what == 2)
       return fail(DRS_ERR_COMM, "table-sharded exchange timed out waiting for a peer rank's "
                                 "flag (a peer died, or ranks served different queries)");
@@ -1166,10 +1181,9 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) try {
     CUB(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
     for (auto& v : ln.ev) CUB(cudaEventCreate(&v));
     CUB(cudaEventCreateWithFlags(&ln.tail, cudaEventDisableTiming));
-    TRYB(dev_alloc_t(e, &ln.d_err, 4));
-    CUB(cudaMemset(ln.d_err, 0, 16));
-    CUB(cudaHostAlloc((void**)&ln.h_err, 16, cudaHostAllocDefault));
-    *ln.h_err = 0;
+    CUB(cudaHostAlloc((void**)&ln.h_err, 64, cudaHostAllocMapped));
+    std::memset(ln.h_err, 0, 64);
+    CUB(cudaHostGetDevicePointer((void**)&ln.d_err, ln.h_err, 0));
   }
   for (auto& v : e->ev_timer) CUB(cudaEventCreate(&v));
 
@@ -1382,6 +1396,7 @@ int drs_destroy(drs_engine* e) try {
   for (Mlp* m : {&e->bot, &e->top, &e->fin, &e->task, &e->rnn[0], &e->rnn[1]})
     for (Layer& l : m->layers) { cudaFree(l.W); cudaFree(l.b); cudaFree(l.Wsplit); }
   for (auto& kv : e->staged) free_input_set(kv.second);
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (int i = 0; i < kMaxLanes; ++i) {
     Lane& ln = e->lanes[i];
     if (!e->gather_into_R) cudaFree(ln.R);
@@ -1390,7 +1405,6 @@ int drs_destroy(drs_engine* e) try {
     cudaFree(ln.seq); cudaFree(ln.rnn_pre); cudaFree(ln.rnn_h0);
     for (auto* v : {&ln.ybot, &ln.ytop, &ln.yfin, &ln.ytask}) for (float* p : *v) cudaFree(p);
     free_input_set(ln.slot);
-    cudaFree(ln.d_err);
     if (ln.h_err) cudaFreeHost(ln.h_err);
     for (auto& v : ln.ev) if (v) cudaEventDestroy(v);
     if (ln.tail) cudaEventDestroy(ln.tail);
@@ -1504,6 +1518,7 @@ int drs_stage_batch(drs_engine* e, int batch_id, const float* dense, const void*
   for (int t = 0; t < T; ++t) if (!owns(e, t)) alloc_counts[t] = 0;
   auto it = e->staged.find(batch_id);
   if (it != e->staged.end()) { free_input_set(it->second); e->staged.erase(it); }
+  drop_graphs(e);                        // captured steps hold the old batch's pointers
   InputSet s;
   const int dense_rows = n_samples;
   Lane& l0 = e->lanes[0];
@@ -1514,11 +1529,6 @@ int drs_stage_batch(drs_engine* e, int batch_id, const float* dense, const void*
   rc = upload_inputs(e, s, l0.stream, dense, idx, idx_is_i64, lengths, n_samples, &n_idx);
   if (rc == DRS_OK) rc = write_descs(e, s, n_idx, l0.stream);
   if (rc == DRS_OK) rc = launch_scan(e, l0.stream, s, n_samples, l0.d_err);
-  if (rc == DRS_OK) {
-    cudaError_t ce = cudaMemcpyAsync(l0.h_err, l0.d_err, sizeof(int), cudaMemcpyDeviceToHost,
-                                     l0.stream);
-    if (ce != cudaSuccess) rc = fail(DRS_ERR_CUDA, "%s", cudaGetErrorString(ce));
-  }
   if (rc == DRS_OK) rc = finish_lane(e, l0);
   if (rc != DRS_OK) { free_input_set(s); return rc; }
   if (s.idx64) { cudaFree(s.idx64); s.idx64 = nullptr; }
@@ -1535,6 +1545,47 @@ static int enqueue_staged_on(drs_engine* e, Lane& ln, int batch_id, int batch_si
             it->second.n, (long long)cap);
   CU(cudaSetDevice(e->device));
   TRY(check_ready(e));
+  // Replay a captured CUDA graph of this exact step when there is one (unsharded engines, no
+  // per-segment profiling in progress); capture it on first use.
+  if (e->use_graphs && e->world == 1 && !e->prof_on) {
+    const int li = (int)(&ln - e->lanes);
+    const auto key = std::make_tuple(li, batch_id, batch_size);
+    auto g = e->graphs.find(key);
+    if (g == e->graphs.end()) {
+      if (e->graphs.size() >= 512) drop_graphs(e);           // bounded: sizes vary per query
+      drs_engine::StepGraph sg;
+      const int64_t before = e->launches;
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(ln.stream, cudaStreamCaptureModeRelaxed);
+      int rc = DRS_OK;
+      if (ce == cudaSuccess) {
+        rc = enqueue_graph(e, ln, it->second, batch_size);
+        ce = cudaStreamEndCapture(ln.stream, &graph);
+      }
+      if (ce == cudaSuccess && rc == DRS_OK && graph)
+        ce = cudaGraphInstantiate(&sg.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (ce != cudaSuccess || rc != DRS_OK || !sg.exec) {
+        // capture is an optimisation: fall back to plain launches for good
+        cudaGetLastError();
+        e->use_graphs = false;
+        e->launches = before;
+        if (rc != DRS_OK) return rc;
+        return enqueue_graph(e, ln, it->second, batch_size);
+      }
+      sg.launches = e->launches - before;
+      sg.rows = ln.last_rows;
+      e->launches = before;
+      g = e->graphs.emplace(key, sg).first;
+    }
+    CU(cudaGraphLaunch(g->second.exec, ln.stream));
+    e->launches += g->second.launches;
+    e->graph_replays += 1;
+    ln.last_inputs = &it->second;
+    ln.last_B = batch_size;
+    ln.last_rows = g->second.rows;
+    return DRS_OK;
+  }
   return enqueue_graph(e, ln, it->second, batch_size);
 }
 
@@ -1857,7 +1908,6 @@ int drs_sparse_lengths_sum(drs_engine* e, int table, const void* idx, int idx_is
   }
   CUC(cudaMemcpyAsync(out, d_out, (size_t)n_segments * D * sizeof(float), cudaMemcpyDeviceToHost,
                       st));
-  CUC(cudaMemcpyAsync(ln.h_err, ln.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   int rc = finish_lane(e, ln);
   cleanup();
   return rc;
@@ -2012,7 +2062,11 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   if (k == "mlp_chain") e->mlp_chain = value != 0;
   else if (k == "gather_ctas_per_sm") e->gather_ctas_per_sm = (int)value;
   else if (k == "tap_hidden") e->tap_hidden = value != 0;
+  else if (k == "cuda_graphs") e->use_graphs = value != 0;
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", key);
+  CU(cudaSetDevice(e->device));
+  TRY(sync_all(e));
+  drop_graphs(e);                        // captured steps baked the old options in
   return DRS_OK;
 } DRS_CATCH
 
@@ -2065,6 +2119,8 @@ int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs)
   }
   e->rank = rank;
   e->world = world;
+  e->ready = false;
+  drop_graphs(e);
   if (e->row_mode) {
     e->row0.assign(e->T, 0);
     e->row1.assign(e->T, 0);

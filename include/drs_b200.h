@@ -225,7 +225,10 @@ int drs_hbm_bytes(const drs_engine* e, int64_t* bytes_allocated);
 /* Runtime options.  "mlp_chain" (default 1): fuse whole FC stacks into one tcgen05 kernel when
  * the shapes allow (tensor-core precisions only).  "tap_hidden" (default 0): in chain mode also
  * store the hidden activations so that drs_fetch_stage can return them.  "gather_ctas_per_sm"
- * (default 4): K1 runs as a persistent kernel with that many CTAs per SM (0 = one CTA per tile). */
+ * (default 4): K1 runs as a persistent kernel with that many CTAs per SM (0 = one CTA per tile).
+ * "cuda_graphs" (default 1): unsharded engines replay a captured CUDA graph for a staged step they
+ * have served before (same lane, batch id and size) — one cudaGraphLaunch instead of 3-4 kernel
+ * launches, which is what bounds the rate of small queries. */
 int drs_set_option(drs_engine* e, const char* key, int64_t value);
 
 /* Per-segment CUDA-event profiling of the served graph, on the engine stream:
