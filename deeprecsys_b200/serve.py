@@ -237,7 +237,9 @@ def sweep(args, rates_ms, n_queries, target_p99_ms=None, ring=False, generators=
     target = float(target_p99_ms if target_p99_ms is not None else args.target_latency)
     h = SystemHarness(args, ring=ring)
     try:
-        rows = [h.run(n_queries, r, seed=17 + i, generators=generators)
+        # at least n_queries per rate, and at least 0.3 s of arrivals (a fast rate would
+        # otherwise be over before the queues reach their steady state)
+        rows = [h.run(max(n_queries, int(300.0 / r)), r, seed=17 + i, generators=generators)
                 for i, r in enumerate(rates_ms)]
     finally:
         h.close()
