@@ -160,6 +160,7 @@ struct Lane {
   const InputSet* last_inputs = nullptr;
   int last_B = 0, last_rows = 0;
   uint32_t epoch = 0;             // sharded exchange epoch on this lane
+  uint32_t* sync_ctr = nullptr;   // CTA counter of the gather's folded exchange tail (device)
 };
 
 }  // namespace
@@ -580,6 +581,9 @@ void plan_gather(int T, int D, int64_t avg_len, bool dot, int* lpr_out, int* SB_
 // Note: making the gather of query i+1 wait for the gather of query i (so that lanes overlap
 // only MLP/copy work with the HBM-bound gather) was measured slower on B200 than letting two
 // gathers share the chip (RMC1 16384 samples, 3 lanes: 60.5 vs 65.6 M inf/s).
+uint32_t* flag_ptr(drs_engine* e, int q, int lane, int which);
+int shard_signal(drs_engine* e, Lane& ln, int which, uint32_t epoch);
+
 bool persistent_gather_ok(const drs_engine* e, bool dot) {
   return e->gather_ctas_per_sm > 0 && !dot && !e->table_major && e->lpr > 0 &&
          (int)e->owned.size() * (e->SB + 1) <= kPersistOffRegs * kSlsThreads &&
@@ -616,6 +620,22 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot,
     } else {
       for (int q = 0; q < e->world; ++q)
         p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_G_off[li]);
+    }
+  }
+  if (e->world > 1) {
+    // the exchange protocol rides in the kernel: consumed-signal + wait at its head,
+    // arrival signal from its last CTA (sls_gather.cuh); a rank that gathers nothing this
+    // query publishes both flags with the stand-alone kernel instead
+    const int li = (int)(&ln - e->lanes);
+    p.sync_counter = ln.sync_ctr;
+    p.epoch = ln.epoch; p.rank = e->rank; p.world = e->world;
+    for (int q = 0; q < e->world; ++q) {
+      p.arrived_flags[q] = flag_ptr(e, q, li, 0);
+      p.consumed_flags[q] = flag_ptr(e, q, li, 1);
+    }
+    if (p.T == 0) {
+      TRY(shard_signal(e, ln, 1, ln.epoch - 1));
+      TRY(shard_signal(e, ln, 0, ln.epoch));
     }
   }
   if (p.T == 0) return DRS_OK;
@@ -696,13 +716,12 @@ int shard_wait(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
   return DRS_OK;
 }
 
-// After K1 on a sharded engine: publish "my peer stores are issued", wait for every peer's, and
+// After K1 on a sharded engine: wait until every peer's K1 has published its arrival flag, and
 // in row mode add the world partial pooled vectors of this rank's samples (rank order) into the
 // gather-output buffer the interaction / MLP kernels read.
 int exchange_after_gather(drs_engine* e, Lane& ln, int rows) {
   if (e->world <= 1) return DRS_OK;
-  TRY(shard_signal(e, ln, 0, ln.epoch));
-  TRY(shard_wait(e, ln, 0, ln.epoch));
+  TRY(shard_wait(e, ln, 0, ln.epoch));       // (the arrival flags were published by K1's tail)
   if (e->row_mode && rows > 0) {
     const int li = (int)(&ln - e->lanes);
     const int TD = e->T * e->D;
@@ -749,8 +768,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
     const int S = ceil_div(B, e->world);
     row0 = e->rank * S;
     rows = B - row0 < 0 ? 0 : (B - row0 < S ? B - row0 : S);
-    ln.epoch += 1;
-    TRY(shard_wait(e, ln, 1, ln.epoch - 1));   // peers consumed what I wrote last time on this lane
+    ln.epoch += 1;      // (K1's head waits until the peers consumed what was written last time)
   }
   // dense rows of this rank inside s.dense
   const float* dense = s.dense ? s.dense + (int64_t)(row0 - s.dense_row0) * e->m_den : nullptr;
@@ -924,7 +942,6 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
   }
   PROF_MARK(3);
   if (e->prof_on && e->prof_n < e->prof_cap) e->prof_n += 1;
-  if (e->world > 1) TRY(shard_signal(e, ln, 1, ln.epoch));   // my buffer may be overwritten
   ln.last_inputs = &s;
   ln.last_B = B;
   ln.last_rows = rows;
@@ -1181,6 +1198,8 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) try {
     CUB(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
     for (auto& v : ln.ev) CUB(cudaEventCreate(&v));
     CUB(cudaEventCreateWithFlags(&ln.tail, cudaEventDisableTiming));
+    TRYB(dev_alloc_t(e, &ln.sync_ctr, 4));
+    CUB(cudaMemset(ln.sync_ctr, 0, 16));
     CUB(cudaHostAlloc((void**)&ln.h_err, 64, cudaHostAllocMapped));
     std::memset(ln.h_err, 0, 64);
     CUB(cudaHostGetDevicePointer((void**)&ln.d_err, ln.h_err, 0));
@@ -1406,6 +1425,7 @@ int drs_destroy(drs_engine* e) try {
     for (auto* v : {&ln.ybot, &ln.ytop, &ln.yfin, &ln.ytask}) for (float* p : *v) cudaFree(p);
     free_input_set(ln.slot);
     if (ln.h_err) cudaFreeHost(ln.h_err);
+    cudaFree(ln.sync_ctr);
     for (auto& v : ln.ev) if (v) cudaEventDestroy(v);
     if (ln.tail) cudaEventDestroy(ln.tail);
     if (ln.stream) cudaStreamDestroy(ln.stream);
