@@ -92,7 +92,7 @@ def parse_args():
                    help="comma list to restrict the secondary block, e.g. rm2,wnd")
     p.add_argument("--no_sharded", action="store_true",
                    help="N>1: skip the table-/row-sharded legs")
-    p.add_argument("--sharded", type=str, default="rm1:table,rm1:row,rm3:table",
+    p.add_argument("--sharded", type=str, default="rm1:table,rm1:table_nccl,rm1:row,rm3:table",
                    help="N>1: comma list of config:mode sharded legs")
     p.add_argument("--no_system", action="store_true",
                    help="skip the Poisson-arrival serving run through the Queue API")
@@ -398,6 +398,12 @@ class Workload(object):
         self.env, self.opts, self.config = env, opts, config
         world = env.world
         self.B, self.nb = int(B), int(nb)                      # B = samples per GPU per step
+        # "table_nccl": table-wise sharding with the UNFUSED exchange baseline — K1 into a local
+        # send slab, one NCCL all-to-all (torch.distributed), unpack kernel — next to "table",
+        # where the exchange is K1's own peer stores
+        self.nccl_exchange = world > 1 and shard == "table_nccl"
+        if self.nccl_exchange:
+            shard = "table"
         self.sharded = world > 1 and shard in ("table", "row")
         self.row_mode = self.sharded and shard == "row"
         self.shard = shard if self.sharded else "replica"
@@ -413,6 +419,9 @@ class Workload(object):
                                shard_mode="row" if self.row_mode else "table", shard_world=world)
         if self.sharded:
             shardlib.connect(self.eng, env.dist)
+        self._xt = {}
+        if self.nccl_exchange:
+            self.eng.set_option("exchange", 1)
         self.only = (set(shardlib.owned_tables(spec.T, env.rank, world))
                      if (self.sharded and not self.row_mode) else None)
         # replica: every rank has its own table contents and queries; sharded: one global model
@@ -436,16 +445,39 @@ class Workload(object):
     def close(self):
         self.eng.close()
 
+    def enqueue(self, batch_id):
+        """One step of this workload (asynchronous)."""
+        if not self.nccl_exchange:
+            return self.eng.enqueue_staged(batch_id, self.GB)
+        import torch
+        send, recv, n, stream = self.eng.exchange_begin(batch_id, self.GB)
+        world = self.env.world
+
+        def view(ptr):
+            t = self._xt.get((ptr, n))
+            if t is None:
+                class _Dev(object):
+                    __cuda_array_interface__ = {"shape": (world * n,), "typestr": "<f4",
+                                                "data": (ptr, False), "version": 2}
+                t = self._xt[(ptr, n)] = torch.as_tensor(_Dev(), device="cuda")
+            return t
+        ext = self._xt.get(stream)
+        if ext is None:
+            ext = self._xt[stream] = torch.cuda.ExternalStream(stream)
+        with torch.cuda.stream(ext):
+            self.env.dist.all_to_all_single(view(recv), view(send))
+        self.eng.exchange_end()
+
     # ---------------------------------------------------------------- value (device-timed)
     def measure_value(self, steps, warmup, clocks=True, min_load_ms=600.0):
         env, eng, nb, GB = self.env, self.eng, self.nb, self.GB
         # set-up pass: every (lane, staged batch) pair of the rotation once, so that the engine's
         # CUDA graphs of the step exist before anything is timed; then the W warm-up steps
         for i in range(self.lanes * nb):
-            eng.enqueue_staged(i % nb, GB)
+            self.enqueue(i % nb)
         eng.sync()
         for i in range(max(3, warmup)):
-            eng.enqueue_staged(i % nb, GB)
+            self.enqueue(i % nb)
         eng.sync()
         launches0 = eng.launch_count()
         sampler = ClockSampler(env.local) if clocks else None
@@ -456,7 +488,7 @@ class Workload(object):
         eng.profile_begin(steps)
         eng.timer_start()
         for i in range(steps):
-            eng.enqueue_staged(i % nb, GB)
+            self.enqueue(i % nb)
         ms_total = eng.timer_stop()
         eng.sync()
         n_prof, pre_ms, gather_ms, post_ms = eng.profile_end()
@@ -473,7 +505,7 @@ class Workload(object):
             ext = int(max(0.0, min_load_ms - ms_total) / max(1e-3, ms_total / steps)) + 1
             ext = min(ext, 20000)
             for i in range(ext):
-                eng.enqueue_staged(i % nb, GB)
+                self.enqueue(i % nb)
                 if i % 64 == 63:
                     eng.sync()
             eng.sync()
@@ -489,7 +521,7 @@ class Workload(object):
         eng = self.eng
         eng.profile_begin(n)
         for i in range(n):
-            eng.enqueue_staged(i % self.nb, self.GB)
+            self.enqueue(i % self.nb)
             eng.sync()
         return eng.profile_end()
 
@@ -743,7 +775,7 @@ class Workload(object):
         from oracle import numpy_oracle as O
         env, spec, eng, GB = self.env, self.spec, self.eng, self.GB
         T, L = spec.T, spec.L
-        eng.enqueue_staged(batch_id, GB)
+        self.enqueue(batch_id)
         eng.sync()
         pooled = eng.fetch_stage(_lib.STAGE_POOLED)          # rows held by this rank
         out = eng.fetch_stage(_lib.STAGE_OUT)
@@ -842,8 +874,11 @@ def run_sharded_leg(env, opts, config, mode):
         roof = w.roofline(val, solo)
         out = {"config": {"workload": workload_text(config, w.spec, w.GB),
                           "global_batch": w.GB,
-                          "parallelism": "%s-sharded x%d, exchange fused into K1 (peer stores over "
-                                         "NVLink), flag barrier" % (mode, env.world),
+                          "parallelism": ("table-sharded x%d, UNFUSED baseline: K1 -> send slab, "
+                                          "one NCCL all_to_all_single, unpack kernel" % env.world)
+                          if w.nccl_exchange else
+                          "%s-sharded x%d, exchange fused into K1 (peer stores over "
+                          "NVLink), flag barrier" % (mode, env.world),
                           "mlp_precision": opts.precision, "lanes": w.lanes},
                "value": val["value"], "unit": UNIT, "ms_per_step": val["ms_per_step"],
                "steps": steps, "gpu_launches": val["launches"],
@@ -991,6 +1026,9 @@ def run_b200(opts):
             shard_legs["table"]["vs_replica"] = shard_legs["table"]["value"] / val["value"]
         if "row" in shard_legs and "value" in shard_legs["row"]:
             shard_legs["row"]["vs_replica"] = shard_legs["row"]["value"] / val["value"]
+        if "value" in shard_legs.get("table", {}) and "value" in shard_legs.get("table_nccl", {}):
+            shard_legs["table"]["vs_unfused_nccl"] = (shard_legs["table"]["value"]
+                                                      / shard_legs["table_nccl"]["value"])
 
     # ---------------- system level
     system = None

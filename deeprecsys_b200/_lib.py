@@ -106,6 +106,9 @@ _SIGNATURES = {
     "drs_host_unregister": (C.c_int, [C.c_void_p]),
     "drs_shard_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "drs_shard_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "drs_exchange_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _PP, _PP,
+                                     C.POINTER(C.c_int64), _PP]),
+    "drs_exchange_end": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

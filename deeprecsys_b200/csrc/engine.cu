@@ -161,6 +161,9 @@ struct Lane {
   int last_B = 0, last_rows = 0;
   uint32_t epoch = 0;             // sharded exchange epoch on this lane
   uint32_t* sync_ctr = nullptr;   // CTA counter of the gather's folded exchange tail (device)
+  float* xsend = nullptr;         // exchange_mode 1: send / receive slabs
+  float* xrecv = nullptr;
+  int x_batch = 0;                // query in the middle of a begin/end pair
 };
 
 }  // namespace
@@ -199,6 +202,13 @@ struct drs_engine {
   std::map<std::tuple<int, int, int>, StepGraph> graphs;
   bool use_graphs = true;
   int64_t graph_replays = 0;
+
+  // "exchange" option = 1 (table-sharded engines): the UNFUSED baseline.  K1 writes the pooled
+  // vectors into a local send slab [world][S][ceil(T/world)*D], the caller runs one all-to-all
+  // on the lane's stream (NCCL through torch.distributed in bench.py), and an unpack kernel
+  // moves the received blocks into the interaction layout (drs_exchange_begin / _end).
+  int exchange_mode = 0;
+  int xlane = -1;             // lane of the exchange in progress
   int64_t submit_seq = 0;
 
   // options (drs_set_option)
@@ -350,6 +360,7 @@ int write_descs(drs_engine* e, InputSet& s, const std::vector<int64_t>& n_idx,
       x.off = s.off + (size_t)t * (s.n + 1);
       x.n_rows = row ? e->row1[t] - e->row0[t] : e->table_rows[t];
       x.dst_col = row ? t * e->D : gather_dst_col(e, t);   // row mode: partial layout [T*D]
+      if (e->exchange_mode == 1 && e->world > 1) x.dst_col = (int)d.size() * e->D;   // send slab
       x.pad_ = t;
       d.push_back(x);
     }
@@ -617,12 +628,17 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot,
       for (int q = 0; q < e->world; ++q)
         p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_part_off[li]) +
                         (int64_t)e->rank * e->spec.max_batch * TD;
+    } else if (e->exchange_mode == 1) {
+      const int64_t ldx = (int64_t)ceil_div(e->T, e->world) * e->D;
+      p.ld_out = ldx;
+      p.vec_store = (e->D % 4 == 0) ? 1 : 0;
+      for (int q = 0; q < e->world; ++q) p.peer_out[q] = ln.xsend + (int64_t)q * p.shard_S * ldx;
     } else {
       for (int q = 0; q < e->world; ++q)
         p.peer_out[q] = reinterpret_cast<float*>(e->peer_slab[q] + e->lane_G_off[li]);
     }
   }
-  if (e->world > 1) {
+  if (e->world > 1 && e->exchange_mode == 0) {
     // the exchange protocol rides in the kernel: consumed-signal + wait at its head,
     // arrival signal from its last CTA (sls_gather.cuh); a rank that gathers nothing this
     // query publishes both flags with the stand-alone kernel instead
@@ -721,6 +737,8 @@ int shard_wait(drs_engine* e, Lane& ln, int which, uint32_t epoch) {
 // gather-output buffer the interaction / MLP kernels read.
 int exchange_after_gather(drs_engine* e, Lane& ln, int rows) {
   if (e->world <= 1) return DRS_OK;
+  if (e->exchange_mode == 1)
+    return fail(DRS_ERR_STATE, "exchange mode 1 serves through drs_exchange_begin / _end");
   TRY(shard_wait(e, ln, 0, ln.epoch));       // (the arrival flags were published by K1's tail)
   if (e->row_mode && rows > 0) {
     const int li = (int)(&ln - e->lanes);
@@ -760,32 +778,49 @@ int check_ready(drs_engine* e) {
 // B = samples of the whole query.  Single GPU: rows = B.  Sharded: this rank runs the dense
 // part on its slice [row0, row0 + rows) and gathers its tables for all B samples.
 // pk: coalesced requests — B stacked rows, dense rows already stacked in `dense_stacked`.
+// phase: 0 = the whole graph; 1 = up to and including K1; 2 = everything after K1 (the two
+// halves of drs_exchange_begin / drs_exchange_end, DLRM only).
 int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
-                  const SlsPackets* pk = nullptr, const float* dense_stacked = nullptr) {
+                  const SlsPackets* pk = nullptr, const float* dense_stacked = nullptr,
+                  int phase = 0) {
   const int D = e->D, T = e->T;
   int row0 = 0, rows = B;
   if (e->world > 1) {
     const int S = ceil_div(B, e->world);
     row0 = e->rank * S;
     rows = B - row0 < 0 ? 0 : (B - row0 < S ? B - row0 : S);
-    ln.epoch += 1;      // (K1's head waits until the peers consumed what was written last time)
+    if (phase != 2) ln.epoch += 1;   // (K1's head waits until the peers consumed the last one)
   }
   // dense rows of this rank inside s.dense
   const float* dense = s.dense ? s.dense + (int64_t)(row0 - s.dense_row0) * e->m_den : nullptr;
   int64_t dense_rows_left = s.dense_rows - (row0 - s.dense_row0);
   if (pk) { dense = dense_stacked; dense_rows_left = e->spec.max_batch; }
   const int64_t cap = e->spec.max_batch;
-  PROF_MARK(0);
+  if (phase != 2) PROF_MARK(0);
   switch (e->spec.model_type) {
     case DRS_MODEL_DLRM: {
-      if (e->dot) TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows,
-                              ln.dense_out, D));
-      else TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows, ln.R,
-                       e->ld_R));
-      PROF_MARK(1);
-      TRY(launch_gather(e, ln, s, B, e->dot, pk));
-      PROF_MARK(2);
-      TRY(exchange_after_gather(e, ln, rows));
+      if (phase != 2) {
+        if (e->dot) TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows,
+                                ln.dense_out, D));
+        else TRY(run_mlp(e, ln, e->bot, ln.ybot, dense, e->m_den, dense_rows_left, rows, ln.R,
+                         e->ld_R));
+        PROF_MARK(1);
+        TRY(launch_gather(e, ln, s, B, e->dot, pk));
+        PROF_MARK(2);
+      }
+      if (phase == 1) break;
+      if (phase == 2) {
+        // received blocks [world][S][ceil(T/world)*D] -> table columns of the interaction buffer
+        const int S = ceil_div(B, e->world), tpr = ceil_div(T, e->world);
+        if (rows > 0) {
+          k_unpack_exchange<<<ew_grid((int64_t)rows * T * D), 256, 0, ln.stream>>>(
+              ln.xrecv, S, tpr, e->world, T, D, rows, ln.G, e->ld_G, gather_dst_col(e, 0));
+          CU(cudaGetLastError());
+          e->launches += 1;
+        }
+      } else {
+        TRY(exchange_after_gather(e, ln, rows));
+      }
       TRY(run_mlp(e, ln, e->top, ln.ytop, ln.R, e->ld_R, cap, rows));
       break;
     }
@@ -940,8 +975,8 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
     default:
       return fail(DRS_ERR_INVALID, "unknown model_type %d", e->spec.model_type);
   }
-  PROF_MARK(3);
-  if (e->prof_on && e->prof_n < e->prof_cap) e->prof_n += 1;
+  if (phase != 1) PROF_MARK(3);
+  if (e->prof_on && e->prof_n < e->prof_cap && phase != 1) e->prof_n += 1;
   ln.last_inputs = &s;
   ln.last_B = B;
   ln.last_rows = rows;
@@ -1426,6 +1461,7 @@ int drs_destroy(drs_engine* e) try {
     free_input_set(ln.slot);
     if (ln.h_err) cudaFreeHost(ln.h_err);
     cudaFree(ln.sync_ctr);
+    cudaFree(ln.xsend); cudaFree(ln.xrecv);
     for (auto& v : ln.ev) if (v) cudaEventDestroy(v);
     if (ln.tail) cudaEventDestroy(ln.tail);
     if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -1819,6 +1855,43 @@ int drs_submit_many(drs_engine* e, int n, const int32_t* batch_ids, const int32_
   return DRS_OK;
 } DRS_CATCH
 
+int drs_exchange_begin(drs_engine* e, int batch_id, int batch_size, void** send, void** recv,
+                       int64_t* floats_per_peer, void** stream) try {
+  CHECK_ARG(e && send && recv && floats_per_peer && stream, "NULL argument");
+  CHECK_ARG(e->exchange_mode == 1 && e->world > 1 && !e->row_mode,
+            "drs_exchange_begin needs a connected table-sharded engine with option exchange = 1");
+  CHECK_ARG(e->spec.model_type == DRS_MODEL_DLRM && !e->dot,
+            "the unfused exchange baseline covers DLRM (cat) only");
+  CHECK_ARG(e->xlane < 0, "an exchange is already in progress");
+  auto it = e->staged.find(batch_id);
+  if (it == e->staged.end()) return fail(DRS_ERR_STATE, "batch %d was not staged", batch_id);
+  CHECK_ARG(batch_size >= 1 && batch_size <= it->second.n &&
+                batch_size <= (int64_t)e->spec.max_batch * e->world,
+            "batch_size %d out of range", batch_size);
+  CU(cudaSetDevice(e->device));
+  TRY(check_ready(e));
+  Lane& ln = pick_lane(e);
+  TRY(enqueue_graph(e, ln, it->second, batch_size, nullptr, nullptr, 1));
+  ln.x_batch = batch_id;
+  e->xlane = (int)(&ln - e->lanes);
+  *send = ln.xsend;
+  *recv = ln.xrecv;
+  *floats_per_peer = (int64_t)ceil_div(batch_size, e->world) * ceil_div(e->T, e->world) * e->D;
+  *stream = (void*)ln.stream;
+  return DRS_OK;
+} DRS_CATCH
+
+int drs_exchange_end(drs_engine* e) try {
+  CHECK_ARG(e, "engine is NULL");
+  CHECK_ARG(e->xlane >= 0, "no exchange in progress");
+  CU(cudaSetDevice(e->device));
+  Lane& ln = e->lanes[e->xlane];
+  e->xlane = -1;
+  auto it = e->staged.find(ln.x_batch);
+  if (it == e->staged.end()) return fail(DRS_ERR_STATE, "batch %d was not staged", ln.x_batch);
+  return enqueue_graph(e, ln, it->second, ln.last_B, nullptr, nullptr, 2);
+} DRS_CATCH
+
 int drs_wait(drs_engine* e, int64_t ticket) try {
   CHECK_ARG(e, "engine is NULL");
   const int lane = (int)(ticket & 0xff);
@@ -2083,6 +2156,23 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   else if (k == "gather_ctas_per_sm") e->gather_ctas_per_sm = (int)value;
   else if (k == "tap_hidden") e->tap_hidden = value != 0;
   else if (k == "cuda_graphs") e->use_graphs = value != 0;
+  else if (k == "exchange") {
+    CHECK_ARG(value == 0 || value == 1, "exchange must be 0 (fused peer stores) or 1 (unfused)");
+    CHECK_ARG(!e->row_mode, "the unfused exchange baseline is table-wise");
+    CU(cudaSetDevice(e->device));
+    TRY(sync_all(e));
+    e->exchange_mode = (int)value;
+    if (value == 1) {
+      const size_t n = (size_t)kMaxShardRanks * e->spec.max_batch *
+                       ceil_div(e->T, 1 > e->world ? 1 : e->world) * e->D;
+      for (int i = 0; i < e->n_lanes; ++i) {
+        Lane& ln = e->lanes[i];
+        if (!ln.xsend) TRY(dev_alloc_t(e, &ln.xsend, n));
+        if (!ln.xrecv) TRY(dev_alloc_t(e, &ln.xrecv, n));
+      }
+    }
+    TRY(rewrite_all_descs(e));
+  }
   else return fail(DRS_ERR_INVALID, "unknown option '%s'", key);
   CU(cudaSetDevice(e->device));
   TRY(sync_all(e));

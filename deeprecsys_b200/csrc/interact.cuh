@@ -68,6 +68,23 @@ __global__ void k_sum_units(const float* __restrict__ units, int64_t unit_stride
   }
 }
 
+// Unfused exchange baseline: recv = [world][S][tpr*D] blocks (block q = this rank's samples x
+// the tables rank q owns, table q + j*world at columns j*D) -> out[row, col0 + t*D ...].
+__global__ void k_unpack_exchange(const float* __restrict__ recv, int S, int tpr, int world, int T,
+                                  int D, int rows, float* __restrict__ out, int64_t ld_out,
+                                  int col0) {
+  const int64_t n = (int64_t)rows * T * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / ((int64_t)T * D);
+    const int r = (int)(i - row * (int64_t)T * D);
+    const int t = r / D, c = r - t * D;
+    const int q = t % world, j = t / world;
+    out[row * ld_out + col0 + (int64_t)t * D + c] =
+        recv[((int64_t)q * S + row) * ((int64_t)tpr * D) + (int64_t)j * D + c];
+  }
+}
+
 constexpr int kStackMaxSrc = 32;
 struct StackRows {
   int n;                                  // requests

@@ -305,6 +305,18 @@ class AccelEngine(object):
         _lib.check(self.lib.drs_shard_connect(self._handle, int(rank), int(world), arr))
         self.rank, self.world = int(rank), int(world)
 
+    def exchange_begin(self, batch_id, batch_size):
+        """Unfused-exchange baseline, first half (``set_option("exchange", 1)``):
+        -> (send address, recv address, floats per peer, cudaStream_t)."""
+        send, recv, stream, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.drs_exchange_begin(self._handle, int(batch_id), int(batch_size),
+                                               C.byref(send), C.byref(recv), C.byref(n),
+                                               C.byref(stream)))
+        return send.value, recv.value, n.value, stream.value
+
+    def exchange_end(self):
+        _lib.check(self.lib.drs_exchange_end(self._handle))
+
     def launch_count(self):
         n = C.c_int64()
         _lib.check(self.lib.drs_launch_count(self._handle, C.byref(n)))

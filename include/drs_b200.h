@@ -228,7 +228,8 @@ int drs_hbm_bytes(const drs_engine* e, int64_t* bytes_allocated);
  * (default 4): K1 runs as a persistent kernel with that many CTAs per SM (0 = one CTA per tile).
  * "cuda_graphs" (default 1): unsharded engines replay a captured CUDA graph for a staged step they
  * have served before (same lane, batch id and size) — one cudaGraphLaunch instead of 3-4 kernel
- * launches, which is what bounds the rate of small queries. */
+ * launches, which is what bounds the rate of small queries.  "exchange" (default 0): 1 selects
+ * the unfused exchange baseline of drs_exchange_begin / drs_exchange_end. */
 int drs_set_option(drs_engine* e, const char* key, int64_t value);
 
 /* Per-segment CUDA-event profiling of the served graph, on the engine stream:
@@ -270,6 +271,20 @@ int drs_host_unregister(void* ptr);
 #define DRS_SHARD_BLOB_BYTES 192
 int drs_shard_export(drs_engine* e, void* blob_out);
 int drs_shard_connect(drs_engine* e, int rank, int world, const void* all_blobs);
+
+/* Unfused exchange BASELINE for table-wise sharding (SURVEY 2a/8e name a single NCCL all-to-all;
+ * the product fuses the exchange into K1's stores instead, see above).  After
+ * drs_set_option(e, "exchange", 1) a staged DLRM query is served in two halves around a
+ * collective the caller runs on the returned stream:
+ *   drs_exchange_begin: bottom MLP + K1 -> pooled vectors into a local send slab
+ *                       [world][ceil(B/world)][ceil(T/world)*D] (block q = rank q's samples)
+ *   caller:             all-to-all of floats_per_peer floats per peer, send -> recv, on `stream`
+ *                       (bench.py: torch.distributed.all_to_all_single over NCCL)
+ *   drs_exchange_end:   unpack the received blocks into the interaction layout + top MLP
+ * It exists so that the cost of not fusing can be measured next to the fused path. */
+int drs_exchange_begin(drs_engine* e, int batch_id, int batch_size, void** send, void** recv,
+                       int64_t* floats_per_peer, void** stream);
+int drs_exchange_end(drs_engine* e);
 
 #ifdef __cplusplus
 }

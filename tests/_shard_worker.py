@@ -26,6 +26,8 @@ def main():
     mode = sys.argv[2] if len(sys.argv) > 2 else "table"
     if mode == "row":
         return main_row(rank, world, local, precision)
+    if mode == "nccl":
+        return main_nccl(rank, world, local, precision)
     for name in ("dlrm_cat", "wnd", "ncf", "din_many", "dlrm_rm3_like", "mtwnd"):
         mb = 24 if name == "dlrm_rm3_like" else 96
         c = make_case(name, num_batches=2, max_batch=mb)       # same seed on every rank
@@ -64,6 +66,61 @@ def main():
         eng.close()
         if rank == 0:
             print("sharded %s ok on %d GPUs (%s)" % (name, world, precision))
+    dist.destroy_process_group()
+    print("RANK %d DONE" % rank)
+
+
+def main_nccl(rank, world, local, precision):
+    """The UNFUSED exchange baseline (drs_exchange_begin / NCCL all_to_all_single /
+    drs_exchange_end) must give what the fused peer-store exchange gives: pooled slices
+    bit-exact, outputs equal to the oracle."""
+    for name in ("dlrm_cat", "dlrm_rm3_like", "dlrm_rm2_like"):
+        mb = 24 if name == "dlrm_rm3_like" else 96
+        c = make_case(name, num_batches=2, max_batch=mb)
+        S = shard.slice_size(mb, world)
+        eng = AccelEngine(args=c.args, device=local, max_batch=S, precision=precision,
+                          max_lookups_per_table=mb * max(1, c.spec.L))
+        shard.connect(eng, dist)
+        eng.set_option("exchange", 1)
+        for t in shard.owned_tables(c.spec.T, rank, world):
+            eng.load_table(t, c.tables[t])
+        for (mlp_id, layer), (W, b) in c.fcs.items():
+            eng.load_fc(mlp_id, layer, W, b)
+        for j in range(2):
+            dense, ids, lengths = request(c, j, mb)
+            eng.stage_batch(j, dense, ids, lengths)
+        dist.barrier()
+        views = {}
+        for rep in range(3):
+            for batch_id, B in [(0, mb), (1, mb - 5), (0, 3)]:
+                dense, ids, lengths = request(c, batch_id, B)
+                st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+                row0, rows = shard.sample_slice(B, rank, world)
+                send, recv, n, stream = eng.exchange_begin(batch_id, B)
+
+                def view(ptr):
+                    if (ptr, n) not in views:
+                        class _Dev(object):
+                            __cuda_array_interface__ = {"shape": (world * n,), "typestr": "<f4",
+                                                        "data": (ptr, False), "version": 2}
+                        views[(ptr, n)] = torch.as_tensor(_Dev(), device="cuda")
+                    return views[(ptr, n)]
+                with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                    dist.all_to_all_single(view(recv), view(send))
+                eng.exchange_end()
+                eng.sync()
+                out = eng.fetch_stage(_lib.STAGE_OUT) if rows > 0 else np.zeros((0, c.spec.out_dim))
+                np.testing.assert_allclose(out[:rows], st["out"][row0:row0 + rows], rtol=1e-4,
+                                           atol=1e-5)
+                if rows > 0:
+                    pooled = eng.fetch_stage(_lib.STAGE_POOLED)
+                    want = st["pooled"][row0:row0 + rows]
+                    assert np.array_equal(pooled.view(np.uint32), want.view(np.uint32)), \
+                        "%s: pooled slice not bit-exact on rank %d (nccl exchange)" % (name, rank)
+        dist.barrier()
+        eng.close()
+        if rank == 0:
+            print("nccl-exchange %s ok on %d GPUs (%s)" % (name, world, precision))
     dist.destroy_process_group()
     print("RANK %d DONE" % rank)
 

@@ -83,7 +83,9 @@ def test_single_gpu_line_carries_every_secondary_config():
 
 def test_two_ranks_over_gloo_run_the_sharded_legs_with_parity():
     port = str(29700 + os.getpid() % 200)
-    procs = [_run(["--gpus", "2"] + COMMON + ["--no_e2e", "--no_sweep"],
+    # (the unfused NCCL-exchange leg needs real device buffers: not part of the dry run)
+    procs = [_run(["--gpus", "2"] + COMMON + ["--no_e2e", "--no_sweep", "--sharded",
+                                             "rm1:table,rm1:row,rm3:table"],
                   env={"RANK": str(r), "LOCAL_RANK": str(r), "WORLD_SIZE": "2",
                        "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": port}) for r in range(2)]
     outs = [_finish(p) for p in procs]

@@ -46,3 +46,19 @@ def test_row_sharded_matches_oracle(world, precision):
                           text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-4000:]
     assert proc.stdout.count("DONE") == world, proc.stdout[-4000:]
+
+
+@pytest.mark.parametrize("world,precision", [(2, "fp32"), (4, "tf32x3"), (8, "fp32")])
+def test_unfused_nccl_exchange_baseline_matches_oracle(world, precision):
+    """drs_exchange_begin / all_to_all_single over NCCL / drs_exchange_end: the baseline the
+    fused exchange is measured against computes the same thing."""
+    n = _ngpu()
+    if n < world:
+        pytest.skip("needs >= %d GPUs (have %d)" % (world, n))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", "29651",
+           os.path.join(ROOT, "tests", "_shard_worker.py"), precision, "nccl"]
+    proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-4000:]
+    assert proc.stdout.count("DONE") == world, proc.stdout[-4000:]
