@@ -216,6 +216,8 @@ struct drs_engine {
   int n_sm = 148;
   bool mlp_chain = true;      // fuse whole MLP stacks into one tcgen05 kernel when shapes allow
   bool tap_hidden = false;    // chain mode: also store hidden activations for drs_fetch_stage
+  int tc_persistent = 1;      // k_fc_tc_persist: 0 never, 1 for grids of more than one wave,
+                              // n >= 2 always, with at most n CTAs
 
   // gather launch geometry
   int lpr = 0, SB = 1, idx_cap = 0;
@@ -418,7 +420,7 @@ int launch_fc(drs_engine* e, Lane& ln, const Layer& l, const float* X, int64_t l
     q.Y = Y; q.ldy = ldy; q.y_bstride = y_bstride;
     q.M = M; q.N = l.out; q.K = l.in; q.act = l.act;
     q.split3 = (e->spec.precision == DRS_PREC_TF32X3);
-    int rc = tc_fc_launch(q, l.n_units, ln.stream);
+    int rc = tc_fc_launch(q, l.n_units, ln.stream, e->tc_persistent);
     if (rc != 0) return fail(DRS_ERR_CUDA, "tensor-core FC launch failed: %s",
                              cudaGetErrorString((cudaError_t)rc));
     e->launches += 1;
@@ -2156,6 +2158,7 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   else if (k == "gather_ctas_per_sm") e->gather_ctas_per_sm = (int)value;
   else if (k == "tap_hidden") e->tap_hidden = value != 0;
   else if (k == "cuda_graphs") e->use_graphs = value != 0;
+  else if (k == "tc_persistent") e->tc_persistent = (int)value;
   else if (k == "exchange") {
     CHECK_ARG(value == 0 || value == 1, "exchange must be 0 (fused peer stores) or 1 (unfused)");
     CHECK_ARG(!e->row_mode, "the unfused exchange baseline is table-wise");

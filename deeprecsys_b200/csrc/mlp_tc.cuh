@@ -318,6 +318,216 @@ k_fc_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtens
   }
 }
 
+// ------------------------------------------------------------------ persistent variant
+// Same arithmetic and tiles as k_fc_tc, restructured so that the tensor pipe does not idle
+// between tiles (one CTA per tile paid TMEM allocation, the pipeline
+// fill and a ~10 us register/smem epilogue per tile with nothing overlapping them — the pipe was
+// 73 % busy on Wide&Deep's 1376 -> 1024 layer):
+//   * one CTA per SM loops over its tiles (tile = blockIdx.x + i * gridDim.x, n fastest so that
+//     neighbouring CTAs read the same X rows out of L2);
+//   * TWO accumulators in TMEM (2 x BN columns): the MMA warp starts tile i+1 while the epilogue
+//     warps drain tile i;
+//   * the smem ring runs across tile boundaries (the first chunks of tile i+1 are loading while
+//     tile i's last MMAs retire);
+//   * dedicated epilogue warps (6..9) with their own staging tile, so the transform warps (2..5)
+//     keep splitting X chunks of the next tile; in single-pass tf32 mode the MMA warp consumes
+//     the TMA barrier directly and the transform warps stay out of the loop.
+constexpr int kTcPThreads = 320;                 // TMA, MMA, 4 transform, 4 epilogue warps
+constexpr int kTcPStageTile = 32 * 33 * 4;       // per epilogue warp: 32 rows x 33 floats
+
+__host__ __device__ constexpr int tcp_stages(int bn) {
+  return (200 * 1024) / tc_stage_bytes(bn) > 8 ? 8 : (200 * 1024) / tc_stage_bytes(bn);
+}
+__host__ __device__ constexpr int tcp_smem_bytes(int bn) {
+  return tcp_stages(bn) * tc_stage_bytes(bn) + 4 * kTcPStageTile + 1024 /*align*/ + 512 /*barriers*/;
+}
+
+struct TcTileGrid { int tiles_n, tiles_m, units; };
+
+template <int BN>
+__global__ void __launch_bounds__(kTcPThreads, 1)
+k_fc_tc_persist(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
+                const TcFcParams p, const TcTileGrid tg) {
+  constexpr int STAGES = tcp_stages(BN);
+  constexpr int A_BYTES = kTcBM * kTcBK * 4;
+  constexpr int B_BYTES = BN * kTcBK * 4;
+  constexpr int STAGE_BYTES = tc_stage_bytes(BN);
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;          // columns of one accumulator
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;              // power of two, <= 512
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* tiles = base;
+  float* stage_tiles = reinterpret_cast<float*>(base + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES +
+                                               4 * kTcPStageTile);
+  uint64_t* full = bars;                    // TMA -> transform (tf32x3) / MMA (tf32)
+  uint64_t* xfrm = bars + STAGES;           // transform -> MMA
+  uint64_t* empty = bars + 2 * STAGES;      // MMA -> TMA
+  uint64_t* acc_full = bars + 3 * STAGES;   // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;       // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int nk = (p.K + kTcBK - 1) / kTcBK;
+  const int ntiles = tg.tiles_n * tg.tiles_m * tg.units;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&xfrm[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);          // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: chunks of all my tiles, one continuous ring
+    if (lane == 0) {
+      const uint32_t tx = A_BYTES + (p.split3 ? 2 : 1) * B_BYTES;
+      int c = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tn = tile % tg.tiles_n, tm = (tile / tg.tiles_n) % tg.tiles_m;
+        const int z = tile / (tg.tiles_n * tg.tiles_m);
+        const int xrow = z * p.x_rows_per_unit + tm * kTcBM;
+        const int wrow = z * p.w_rows_per_unit + tn * BN;
+        for (int kc = 0; kc < nk; ++kc, ++c) {
+          const int s = c % STAGES, u = c / STAGES;
+          if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
+          unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], tx);
+          tma_load_2d(st, &mapX, kc * kTcBK, xrow, &full[s]);
+          tma_load_2d(st + 2 * A_BYTES, &mapW, kc * kTcBK, wrow, &full[s]);
+          if (p.split3)
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapW, kc * kTcBK, wrow + p.N, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulators ping-pong between two TMEM regions
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BN);
+      uint64_t* ready = p.split3 ? xfrm : full;
+      int c = 0, t = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        if (t >= 2) {                        // the epilogue of tile t-2 has drained this region
+          mbar_wait(&acc_empty[buf], (uint32_t)(((t >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)buf * ACC_COLS;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < nk; ++kc, ++c) {
+          const int s = c % STAGES, u = c / STAGES;
+          mbar_wait(&ready[s], (uint32_t)(u & 1));
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+          const uint32_t a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES;
+          const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+          for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
+            const uint32_t koff = (uint32_t)(k * kTcUmmaK * 4);
+            if (p.split3) {
+              umma_tf32(tacc, umma_desc_sw128(a_lo + koff), umma_desc_sw128(b_hi + koff), idesc, acc);
+              acc = 1;
+              umma_tf32(tacc, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_lo + koff), idesc, 1);
+            }
+            umma_tf32(tacc, umma_desc_sw128(a_hi + koff), umma_desc_sw128(b_hi + koff), idesc, acc);
+            acc = 1;
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== transform warps (2..5): tf32x3 only — split the landed X chunk into hi / lo in place
+    if (p.split3) {
+      const int tt = threadIdx.x - 2 * kWarp;          // 0..127
+      int c = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nk; ++kc, ++c) {
+          const int s = c % STAGES, u = c / STAGES;
+          mbar_wait(&full[s], (uint32_t)(u & 1));
+          float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(tiles + (size_t)s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+          for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+            const int i = j * 128 + tt;
+            const float4 v = hi[i];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            hi[i] = h;
+            lo[i] = l;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xfrm[s]);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (6..9): TMEM -> registers -> staging tile -> coalesced stores
+    const int q = warp % 4;                            // TMEM lane quarter this warp may access
+    float* stg = stage_tiles + (size_t)(warp - 6) * 32 * 33;
+    constexpr int CH = BN >= 32 ? 32 : 16;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      const int tn = tile % tg.tiles_n, tm = (tile / tg.tiles_n) % tg.tiles_m;
+      const int z = tile / (tg.tiles_n * tg.tiles_m);
+      const int n0 = tn * BN, row0 = tm * kTcBM + q * 32;
+      float* __restrict__ ybase = p.Y + (int64_t)z * p.y_bstride;
+      const float* __restrict__ bias = p.bias + (int64_t)z * p.b_bstride;
+      mbar_wait(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t r[CH];
+        const uint32_t taddr = tmem_base + (uint32_t)buf * ACC_COLS + ((uint32_t)(q * 32) << 16) +
+                               (uint32_t)c0;
+        if (CH == 32) tmem_ld_32x32b_x32(taddr, r);
+        else tmem_ld_32x32b_x16(taddr, r);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        if (lane < CH && n < p.N) {
+          const float bn_ = __ldg(bias + n);
+          const int rmax = min(32, p.M - row0);
+          for (int rr = 0; rr < rmax; ++rr)
+            ybase[(int64_t)(row0 + rr) * p.ldy + n] = apply_act(stg[rr * 33 + lane] + bn_, p.act);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);     // this warp's quarter is drained
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // W [n] -> Wsplit[0][n] = top 19 bits, Wsplit[1][n] = W - hi   (per unit: [2][N*K])
 __global__ void k_split_tf32(const float* __restrict__ W, float* __restrict__ out, int64_t count) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
@@ -405,6 +615,38 @@ inline bool tc_fc_supported(int N, int K, int64_t ldx, const float* X) {
          ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && tc_encode_fn() != nullptr;
 }
 
+inline int tc_sm_count() {
+  static int n_sm[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return 148;
+  if (n_sm[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+      v = 148;
+    n_sm[dev] = v;
+  }
+  return n_sm[dev];
+}
+
+template <int BN>
+inline cudaError_t tc_launch_persist_bn(const CUtensorMap& mx, const CUtensorMap& mw,
+                                        const TcFcParams& p, dim3 grid, cudaStream_t stream,
+                                        int max_ctas) {
+  static std::atomic<uint64_t> attr{0};
+  if (first_use_on_device(attr)) {
+    cudaError_t e = cudaFuncSetAttribute(k_fc_tc_persist<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tcp_smem_bytes(BN));
+    if (e != cudaSuccess) return e;
+  }
+  TcTileGrid tg{(int)grid.x, (int)grid.y, (int)grid.z};
+  const int ntiles = tg.tiles_n * tg.tiles_m * tg.units;
+  int ctas = ntiles < tc_sm_count() ? ntiles : tc_sm_count();
+  if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
+  k_fc_tc_persist<BN><<<ctas, kTcPThreads, tcp_smem_bytes(BN), stream>>>(mx, mw, p, tg);
+  return cudaGetLastError();
+}
+
 template <int BN>
 inline cudaError_t tc_launch_bn(const CUtensorMap& mx, const CUtensorMap& mw, const TcFcParams& p,
                                 dim3 grid, cudaStream_t stream) {
@@ -419,7 +661,10 @@ inline cudaError_t tc_launch_bn(const CUtensorMap& mx, const CUtensorMap& mw, co
 }
 
 // returns a cudaError_t value (0 = ok); cudaErrorInvalidValue if the tensor map cannot be built
-inline int tc_fc_launch(const TcFcLaunch& q, int n_units, cudaStream_t stream) {
+// persistent: 0 = one CTA per tile; 1 = persistent tiles when the grid exceeds one wave;
+// n >= 2 = always persistent with at most n CTAs (tests: many tiles per CTA on small problems)
+inline int tc_fc_launch(const TcFcLaunch& q, int n_units, cudaStream_t stream,
+                        int persistent = 1) {
   const int bn = tc_pick_bn(q.N);
   CUtensorMap mx, mw;
   if (!tc_make_map(&mx, q.X, q.x_rows, q.K, q.ldx, kTcBM)) return (int)cudaErrorInvalidValue;
@@ -433,6 +678,18 @@ inline int tc_fc_launch(const TcFcLaunch& q, int n_units, cudaStream_t stream) {
   p.w_rows_per_unit = 2 * q.N;
   p.split3 = q.split3 ? 1 : 0;
   dim3 grid(ceil_div(q.N, bn), ceil_div(q.M, kTcBM), n_units);
+  // persistent tiles pay off once a CTA has more than one tile; a grid that fits one wave keeps
+  // the one-CTA-per-tile kernel (less shared memory: it can share an SM with the gather)
+  if (persistent >= 2 || (persistent == 1 && (int64_t)grid.x * grid.y * grid.z > tc_sm_count())) {
+    const int cap = persistent >= 2 ? persistent : 0;
+    switch (bn) {
+      case 16:  return (int)tc_launch_persist_bn<16>(mx, mw, p, grid, stream, cap);
+      case 32:  return (int)tc_launch_persist_bn<32>(mx, mw, p, grid, stream, cap);
+      case 64:  return (int)tc_launch_persist_bn<64>(mx, mw, p, grid, stream, cap);
+      case 128: return (int)tc_launch_persist_bn<128>(mx, mw, p, grid, stream, cap);
+      default:  return (int)tc_launch_persist_bn<256>(mx, mw, p, grid, stream, cap);
+    }
+  }
   switch (bn) {
     case 16:  return (int)tc_launch_bn<16>(mx, mw, p, grid, stream);
     case 32:  return (int)tc_launch_bn<32>(mx, mw, p, grid, stream);

@@ -229,7 +229,10 @@ int drs_hbm_bytes(const drs_engine* e, int64_t* bytes_allocated);
  * "cuda_graphs" (default 1): unsharded engines replay a captured CUDA graph for a staged step they
  * have served before (same lane, batch id and size) — one cudaGraphLaunch instead of 3-4 kernel
  * launches, which is what bounds the rate of small queries.  "exchange" (default 0): 1 selects
- * the unfused exchange baseline of drs_exchange_begin / drs_exchange_end. */
+ * the unfused exchange baseline of drs_exchange_begin / drs_exchange_end.  "tc_persistent"
+ * (default 1): wide FC layers whose tile grid exceeds one wave run the persistent tcgen05 kernel
+ * (two TMEM accumulators, epilogue of tile i under the MMAs of tile i+1); 0 = one CTA per tile,
+ * n >= 2 = always persistent with at most n CTAs. */
 int drs_set_option(drs_engine* e, const char* key, int64_t value);
 
 /* Per-segment CUDA-event profiling of the served graph, on the engine stream:

@@ -201,3 +201,30 @@ def test_tf32_single_pass_throughput_mode(name):
         np.testing.assert_allclose(out, st["out"], rtol=0, atol=2e-3)
         pooled = eng.fetch_stage(_lib.STAGE_POOLED)
         assert np.array_equal(pooled.view(np.uint32), st["pooled"].view(np.uint32))
+
+
+@pytest.mark.parametrize("precision,atol", [("tf32x3", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("name,ctas", [("wnd", 5), ("wnd", 148), ("dlrm_rm3_like", 3)])
+def test_persistent_tensor_core_fc_many_tiles_per_cta(name, ctas, precision, atol):
+    """k_fc_tc_persist (two TMEM accumulators, ring running across tile boundaries): forced on,
+    with few CTAs so that each one walks many tiles and both accumulator phases wrap several
+    times; outputs and the wide layers' activations against the oracle."""
+    B = 2048
+    c = make_case(name, num_batches=1, max_batch=B)
+    with AccelEngine(args=c.args, max_batch=B, precision=precision) as eng:
+        eng.set_option("tc_persistent", ctas)
+        eng.set_option("mlp_chain", 0)                 # every layer through the FC kernel
+        eng.load_parameters(c.tables, c.fcs)
+        dense, ids, lengths = request(c, 0, B)
+        out, _ = eng.infer(dense, ids, lengths, B)
+        st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+        scale = max(1.0, float(np.abs(st["out"]).max()))
+        np.testing.assert_allclose(out, st["out"], rtol=0, atol=atol * scale)
+        for k, want in enumerate(st["top"][:-1]):
+            got = eng.fetch_stage(_lib.STAGE_TOP, k)
+            np.testing.assert_allclose(got, want, rtol=0,
+                                       atol=(5e-5 if precision == "tf32x3" else 2e-2)
+                                       * max(1.0, float(np.abs(want).max())))
+        eng.set_option("tc_persistent", 0)             # one CTA per tile: same numbers
+        out0, _ = eng.infer(dense, ids, lengths, B)
+        assert np.array_equal(out.view(np.uint32), out0.view(np.uint32))
