@@ -8,5 +8,6 @@ $NV -o tools/bin/hbm_probe tools/hbm_probe.cu
 $NV -o tools/bin/k1_probe tools/k1_probe.cu
 $NV -DDRS_SLS_UNROLL=16 -o tools/bin/k1_probe_u16 tools/k1_probe.cu
 $NV -DDRS_SLS_UNROLL=10 -o tools/bin/k1_probe_u10 tools/k1_probe.cu
+$NV -DDRS_SLS_UNROLL=6 -o tools/bin/k1_probe_u6 tools/k1_probe.cu
 $NV -DDRS_ROW_EVICT_FIRST=1 -o tools/bin/k1_probe_ef tools/k1_probe.cu
 echo built: $(ls tools/bin)

@@ -146,6 +146,28 @@ __global__ void __launch_bounds__(256) k_gather_stream(const StreamParams p) {
   cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------- co-runner
+// Stand-in for the tensor-core MLP kernels that share the chip with the gather in the real step
+// (k_mlp_chain: 128 CTAs x 192 threads, ~160 registers, ~160 KB shared memory, 15 us + 33 us per
+// 16,384-sample step): same footprint, spins on FMAs for `cycles` clocks.
+template <int R>
+__global__ void __launch_bounds__(192, 1) k_dummy_mlp(float* sink, long long cycles) {
+  extern __shared__ float dsm[];
+  float a[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) a[i] = threadIdx.x * 0.001f + i;
+  dsm[threadIdx.x] = a[0];
+  const long long t0 = clock64();
+  do {
+#pragma unroll
+    for (int i = 0; i < R; ++i) a[i] = fmaf(a[i], 1.0001f, 0.5f);
+  } while (clock64() - t0 < cycles);
+  float sum = dsm[(threadIdx.x + 1) % 192];
+#pragma unroll
+  for (int i = 0; i < R; ++i) sum += a[i];
+  if (sum == 1234.5f) *sink = sum;
+}
+
 // ---------------------------------------------------------------- harness
 struct Ctx {
   int T, B, L, D;
@@ -173,6 +195,52 @@ static float time_launches(int reps, const std::function<void()>& launch) {
   CK(cudaEventElapsedTime(&ms, a, b));
   CK(cudaGetLastError());
   return ms / reps;
+}
+
+// K1 launches on stream A while stand-in MLP kernels (2 per K1 launch, like the bottom and the
+// top stack of a step) run on stream B: wall time from a common start to the end of both.
+struct Corun { float k1_ms, all_ms; };
+static Corun time_corun(int reps, const std::function<void(cudaStream_t)>& launch, float* sink,
+                        int mlp_regs_class, size_t mlp_smem, double sm_ghz) {
+  cudaStream_t sa, sb;
+  CK(cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+  cudaEvent_t e0, ea, eb;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
+  auto mlp = [&](double us) {
+    const long long cyc = (long long)(us * 1e3 * sm_ghz);
+    if (mlp_regs_class == 0) k_dummy_mlp<150><<<128, 192, mlp_smem, sb>>>(sink, cyc);
+    else k_dummy_mlp<70><<<128, 192, mlp_smem, sb>>>(sink, cyc);
+  };
+  CK(cudaFuncSetAttribute(k_dummy_mlp<150>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_dummy_mlp<70>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int i = 0; i < 2; ++i) { launch(sa); mlp(15); mlp(33); }
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0, sa));
+  CK(cudaStreamWaitEvent(sb, e0, 0));
+  for (int i = 0; i < reps; ++i) { launch(sa); mlp(15); mlp(33); }
+  CK(cudaEventRecord(ea, sa));
+  CK(cudaEventRecord(eb, sb));
+  CK(cudaStreamWaitEvent(sa, eb, 0));
+  cudaEvent_t eall;
+  CK(cudaEventCreate(&eall));
+  CK(cudaEventRecord(eall, sa));
+  CK(cudaEventSynchronize(eall));
+  Corun r;
+  CK(cudaEventElapsedTime(&r.k1_ms, e0, ea));
+  CK(cudaEventElapsedTime(&r.all_ms, e0, eall));
+  r.k1_ms /= reps; r.all_ms /= reps;
+  CK(cudaGetLastError());
+  cudaStreamDestroy(sa); cudaStreamDestroy(sb);
+  return r;
+}
+
+static void report_corun(const Ctx& c, const char* name, int ctas_per_sm, int depth,
+                         const char* mlp, Corun r) {
+  printf("{\"corun\": \"%s\", \"ctas_per_sm\": %d, \"depth\": %d, \"mlp_standin\": \"%s\", "
+         "\"k1_stream_ms_per_step\": %.4f, \"step_ms\": %.4f, \"step_GBps\": %.1f}\n",
+         name, ctas_per_sm, depth, mlp, r.k1_ms, r.all_ms, c.bytes / (r.all_ms * 1e-3) / 1e9);
+  fflush(stdout);
 }
 
 static bool same_as_ref(const Ctx& c) {
@@ -211,6 +279,43 @@ static void run_prod(Ctx& c, int reps, int ctas_per_sm, bool is_ref) {
     k_sls_gather_persist<8, false><<<grid, kSlsThreads, smem>>>(p);
   });
   if (!is_ref) report(c, "prod", ctas_per_sm, kSlsUnroll, smem, ms, same_as_ref(c));
+}
+
+static void corun_prod(Ctx& c, int reps, int ctas_per_sm, float* sink, double ghz) {
+  SlsLaunch p{};
+  p.tables = c.descs; p.T = c.T; p.B = c.B; p.D = c.D;
+  p.out = c.out; p.ld_out = (int64_t)c.T * c.D;
+  const int groups = kSlsThreads / 8;
+  p.SB = groups / c.T < 1 ? 1 : groups / c.T;
+  p.idx_cap = (p.SB * c.L + 3 + 3) & ~3;
+  p.vec_store = 1; p.err_flag = c.err;
+  const size_t smem = sls_persist_smem_bytes(p.T, p.SB, p.idx_cap, false);
+  int grid = (c.B + p.SB - 1) / p.SB;
+  if (grid > c.n_sm * ctas_per_sm) grid = c.n_sm * ctas_per_sm;
+  auto launch = [&](cudaStream_t st) {
+    k_sls_gather_persist<8, false><<<grid, kSlsThreads, smem, st>>>(p);
+  };
+  report_corun(c, "prod", ctas_per_sm, kSlsUnroll, "160 regs, 160 KB",
+               time_corun(reps, launch, sink, 0, 160 * 1024, ghz));
+  report_corun(c, "prod", ctas_per_sm, kSlsUnroll, "80 regs, 100 KB",
+               time_corun(reps, launch, sink, 1, 100 * 1024, ghz));
+}
+
+template <int S>
+static void corun_stream(Ctx& c, int reps, int ctas_per_sm, float* sink, double ghz) {
+  StreamParams p{};
+  for (int t = 0; t < c.T; ++t) { p.rows[t] = c.rows[t]; p.idx[t] = c.idx[t]; }
+  p.T = c.T; p.B = c.B; p.L = c.L; p.D = c.D; p.out = c.out; p.ld_out = (int64_t)c.T * c.D;
+  const size_t smem = (size_t)S * 256 * 16;
+  if (smem * ctas_per_sm > 220 * 1024) return;
+  CK(cudaFuncSetAttribute(k_gather_stream<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)smem));
+  const int grid = c.n_sm * ctas_per_sm;
+  auto launch = [&](cudaStream_t st) { k_gather_stream<S><<<grid, 256, smem, st>>>(p); };
+  report_corun(c, "stream", ctas_per_sm, S, "160 regs, 160 KB",
+               time_corun(reps, launch, sink, 0, 160 * 1024, ghz));
+  report_corun(c, "stream", ctas_per_sm, S, "80 regs, 100 KB",
+               time_corun(reps, launch, sink, 1, 100 * 1024, ghz));
 }
 
 template <int S>
@@ -276,6 +381,18 @@ int main(int argc, char** argv) {
     run_stream<24>(c, reps, k);
     run_stream<32>(c, reps, k);
     run_stream<48>(c, reps, k);
+  }
+  // the step as the engine runs it: gathers back to back on one stream, MLP stand-ins beside them
+  float* sink;
+  CK(cudaMalloc(&sink, 16));
+  int khz = 0;
+  CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+  const double ghz = khz * 1e-6;
+  for (int k : {3, 4}) corun_prod(c, reps, k, sink, ghz);
+  for (int k : {2, 3, 4, 5, 6}) {
+    corun_stream<8>(c, reps, k, sink, ghz);
+    corun_stream<12>(c, reps, k, sink, ghz);
+    corun_stream<16>(c, reps, k, sink, ghz);
   }
   int herr = 0;
   CK(cudaMemcpy(&herr, c.err, 4, cudaMemcpyDeviceToHost));
