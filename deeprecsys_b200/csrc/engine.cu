@@ -641,20 +641,21 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot,
     }
   }
   if (e->world > 1 && e->exchange_mode == 0) {
-    // the exchange protocol rides in the kernel: consumed-signal + wait at its head,
-    // arrival signal from its last CTA (sls_gather.cuh); a rank that gathers nothing this
-    // query publishes both flags with the stand-alone kernel instead
+    // one one-warp kernel: "my buffer of the previous query on this lane is consumed" to every
+    // peer, then wait for theirs (shard.cuh) — the peer stores below may overwrite those buffers
     const int li = (int)(&ln - e->lanes);
+    ShardFlags f{};
+    for (int q = 0; q < e->world; ++q) f.peer_flags[q] = flag_ptr(e, q, li, 1);
+    f.world = e->world; f.rank = e->rank;
+    k_shard_sync_consumed<<<1, 32, 0, ln.stream>>>(f, ln.epoch - 1, ln.d_err);
+    CU(cudaGetLastError());
+    e->launches += 1;
+    // the arrival signal rides in K1's tail (its last CTA publishes it); a rank that gathers
+    // nothing this query publishes it with the stand-alone kernel instead
     p.sync_counter = ln.sync_ctr;
     p.epoch = ln.epoch; p.rank = e->rank; p.world = e->world;
-    for (int q = 0; q < e->world; ++q) {
-      p.arrived_flags[q] = flag_ptr(e, q, li, 0);
-      p.consumed_flags[q] = flag_ptr(e, q, li, 1);
-    }
-    if (p.T == 0) {
-      TRY(shard_signal(e, ln, 1, ln.epoch - 1));
-      TRY(shard_signal(e, ln, 0, ln.epoch));
-    }
+    for (int q = 0; q < e->world; ++q) p.arrived_flags[q] = flag_ptr(e, q, li, 0);
+    if (p.T == 0) TRY(shard_signal(e, ln, 0, ln.epoch));
   }
   if (p.T == 0) return DRS_OK;
   int grid = pk ? pk->tile_off[pk->n] : ceil_div(B, e->SB);
@@ -791,7 +792,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
     const int S = ceil_div(B, e->world);
     row0 = e->rank * S;
     rows = B - row0 < 0 ? 0 : (B - row0 < S ? B - row0 : S);
-    if (phase != 2) ln.epoch += 1;   // (K1's head waits until the peers consumed the last one)
+    if (phase != 2) ln.epoch += 1;
   }
   // dense rows of this rank inside s.dense
   const float* dense = s.dense ? s.dense + (int64_t)(row0 - s.dense_row0) * e->m_den : nullptr;

@@ -59,4 +59,32 @@ __global__ void k_shard_wait(const uint32_t* own_flags, int world, uint32_t epoc
   __threadfence_system();
 }
 
+// Before a query's peer stores on a lane: publish "the buffer I filled for the previous query on
+// this lane has been consumed" (true by stream order: its MLPs are done) to every peer, THEN wait
+// until every peer has published the same — signal before wait, so ranks never wait on each
+// other's waits.  One warp: it can spin without holding an SM's worth of resources.
+__global__ void k_shard_sync_consumed(const ShardFlags f, uint32_t epoch_done, int* comm_err_flag) {
+  const int q = threadIdx.x;
+  if (q < f.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.peer_flags[q] + f.rank),
+                 "r"(epoch_done)
+                 : "memory");
+    const uint32_t* own = f.peer_flags[f.rank] + q;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(own) : "memory");
+      if ((int32_t)(v - epoch_done) >= 0) break;
+      if (global_timer_ns() - t0 > kShardWaitTimeoutNs) {
+        if (comm_err_flag) *comm_err_flag = 2;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
 }  // namespace drs

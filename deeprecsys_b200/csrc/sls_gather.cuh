@@ -89,40 +89,17 @@ struct SlsLaunch {
   // instantiation walks kSlsShort segments per lane group at once
   int short_seg;
   SlsPackets pk;          // MULTI instantiation of the persistent kernel only
-  // Sharded exchange, folded into this kernel (shard_S > 0 and sync_counter != nullptr):
-  //   head  publish "my buffer of epoch-1 on this lane is consumed" to every peer (by stream
-  //         order the MLPs that read it have finished), then — before the first peer store —
-  //         wait until every peer has published the same for its buffer;
-  //   tail  the last CTA to finish publishes "my stores of `epoch` are issued" to every peer.
-  // Only the wait for the peers' arrival stays a (one-warp) kernel of its own (shard.cuh).
+  // Sharded exchange (shard_S > 0 and sync_counter != nullptr): the last CTA to finish publishes
+  // "my stores of `epoch` are issued" to every peer — the arrival signal rides in the kernel's
+  // tail instead of a launch of its own.  Nothing in this kernel WAITS for a peer: a persistent
+  // kernel that spins on remote progress while it holds the SMs could starve the very kernel
+  // (another lane's) whose signal a peer is waiting for.  The waits are one-warp kernels
+  // (shard.cuh).
   uint32_t* sync_counter;               // device-local CTA counter, returns to 0 after every launch
   uint32_t epoch;
   int rank, world;
   uint32_t* arrived_flags[kMaxShardRanks];    // peer q's arrived[] array (peer-mapped)
-  uint32_t* consumed_flags[kMaxShardRanks];   // peer q's consumed[] array (peer-mapped)
 };
-
-// head of a sharded gather: see SlsLaunch.  Called by every CTA before its first peer store.
-__device__ __forceinline__ void sls_shard_head(const SlsLaunch& p) {
-  if (p.shard_S <= 0 || p.sync_counter == nullptr) return;
-  const int q = threadIdx.x;
-  if (blockIdx.x == 0 && q < p.world)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.consumed_flags[q] + p.rank),
-                 "r"(p.epoch - 1u)
-                 : "memory");
-  if (q < p.world) {
-    const uint32_t* own = p.consumed_flags[p.rank] + q;
-    const uint64_t t0 = global_timer_ns();
-    uint32_t v;
-    for (;;) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(own) : "memory");
-      if ((int32_t)(v - (p.epoch - 1u)) >= 0) break;
-      if (global_timer_ns() - t0 > kShardWaitTimeoutNs) { *p.err_flag = 2; break; }
-      __nanosleep(100);
-    }
-  }
-  __syncthreads();
-}
 
 // tail of a sharded gather: the last CTA publishes the arrival flags.
 __device__ __forceinline__ void sls_shard_tail(const SlsLaunch& p) {
@@ -303,8 +280,6 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather(const SlsLaunch p) {
     }
   }
   if (use_smem_idx) mbar_wait(bar, 0);
-
-  if (!FUSE_DOT) sls_shard_head(p);
 
   // 3. gather: lane groups walk segments
   const int nseg = sbe * T;
@@ -532,7 +507,6 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
   load_offs(tile + gridDim.x, regs);               // offsets of the next tile stay in registers
   __syncthreads();
   if (use_smem_idx) issue_spans(tile, 0);
-  sls_shard_head(p);                               // (no-op unless sharded) before any peer store
 
   for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
     const int cur = it & 1, nxt = cur ^ 1;
