@@ -76,7 +76,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// DRS_CHAIN_MIN_CTAS: min resident CTAs per SM the compiler must allow (register cap =
+// 65536 / (192 * n)): 1 = unconstrained (~160 registers); 4 = 80 registers, which lets a chain
+// CTA share an SM with three persistent gather CTAs (3 x 16,384 registers) at the price of
+// spills in the epilogue (tools/build_variants.sh builds both for A/B runs).
+#ifndef DRS_CHAIN_MIN_CTAS
+#define DRS_CHAIN_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kTcThreads, DRS_CHAIN_MIN_CTAS)
 k_mlp_chain(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW0,
             const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
             const __grid_constant__ CUtensorMap mapW3, const ChainParams p) {
