@@ -230,17 +230,18 @@ def run_system(args, n_queries, arrival_ms, seed=0, warmup_queries=20):
         h.close()
 
 
-def sweep(args, rates_ms, n_queries, target_p99_ms=None, ring=False, generators=1):
+def sweep(args, rates_ms, n_queries, target_p99_ms=None, ring=False, generators=1,
+          min_seconds=0.0):
     """Run the experiment at each mean inter-arrival time against ONE engine process; report
     the best throughput whose p99 meets ``target_p99_ms`` (args.target_latency by default).
     ``ring``: requests carry their inputs through a shared-memory ring (TensorServiceRequest)."""
     target = float(target_p99_ms if target_p99_ms is not None else args.target_latency)
     h = SystemHarness(args, ring=ring)
     try:
-        # at least n_queries per rate, and at least 0.3 s of arrivals (a fast rate would
+        # at least n_queries per rate, and at least min_seconds of arrivals (a fast rate would
         # otherwise be over before the queues reach their steady state)
-        rows = [h.run(max(n_queries, int(300.0 / r)), r, seed=17 + i, generators=generators)
-                for i, r in enumerate(rates_ms)]
+        rows = [h.run(max(n_queries, int(1000.0 * min_seconds / r)), r, seed=17 + i,
+                      generators=generators) for i, r in enumerate(rates_ms)]
     finally:
         h.close()
     ok = [r for r in rows if r["p99_ms"] <= target and r["failed"] == 0]
@@ -277,7 +278,7 @@ def main(argv=None):
     if not args.model_name:
         args.model_name = {"dlrm": "rm1"}.get(args.model_type, args.model_type)
     rates = rates or [args.avg_arrival_rate]
-    out = sweep(args, rates, n_queries, ring=ring, generators=generators)
+    out = sweep(args, rates, n_queries, ring=ring, generators=generators, min_seconds=0.3)
     print(json.dumps(out))
     return 0
 
