@@ -72,6 +72,9 @@ class AccelBackend(object):
                                   max_lookups_per_table=cap
                                   * max(1, int(args.num_indices_per_lookup)))
         self.stack_rows = cap
+        # query sizes vary from packet to packet: a (lane, batch, size) step hardly ever repeats,
+        # so capturing CUDA graphs of single steps would only cost; load is absorbed by coalescing
+        self.engine.set_option("cuda_graphs", 0)
         self.engine.create()                               # tables -> MLPs, reference draw order
         self.spec = self.engine.spec
         self.upload = bool(getattr(args, "accel_upload_inputs", False))

@@ -691,4 +691,21 @@ __global__ void k_unpack_ids(const uint32_t* __restrict__ packed, int bits, int6
   }
 }
 
+// T equally spaced packed streams (stride_words apart) -> T equally spaced int32 arrays
+__global__ void k_unpack_ids_multi(const uint32_t* __restrict__ packed, int64_t stride_words,
+                                   int bits, int64_t n, int T, int32_t* __restrict__ dst,
+                                   int64_t dst_stride) {
+  const uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  const int64_t total = n * T;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < total;
+       j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = j / n, i = j - t * n;
+    const uint32_t* p = packed + t * stride_words;
+    const int64_t bit = i * bits;
+    const int64_t w = bit >> 5;
+    const uint64_t win = (uint64_t)__ldg(p + w) | ((uint64_t)__ldg(p + w + 1) << 32);
+    dst[t * dst_stride + i] = (int32_t)((uint32_t)(win >> (bit & 31)) & mask);
+  }
+}
+
 }  // namespace drs

@@ -37,6 +37,19 @@ def test_packed_upload_equals_int32_upload(name):
                                   want_pooled.view(np.uint32))
             assert sum(p.nbytes for p in packed) < sum(i.astype(np.int32).nbytes for i in ids) \
                 or B == 1
+            # equally spaced streams in one [T, words] buffer: one copy + one widening kernel
+            if len({len(i) for i in ids}) == 1 and len(set(bits)) == 1 and T > 1:
+                slab, _s = pinned_empty((T, max(len(p) for p in packed)), np.uint32)
+                for t in range(T):
+                    slab[t, :len(packed[t])] = packed[t]
+                out[:] = np.nan
+                eng.enqueue_host_packed(
+                    dptr, (C.c_void_p * T)(*[slab[t].ctypes.data for t in range(T)]),
+                    (C.c_int32 * T)(*bits),
+                    (C.c_void_p * T)(*[l.ctypes.data for l in lengths]), B,
+                    C.c_void_p(out.ctypes.data))
+                eng.sync()
+                assert np.array_equal(np.array(out[:B]).view(np.uint32), want.view(np.uint32))
 
 
 def test_packed_ids_are_validated():
