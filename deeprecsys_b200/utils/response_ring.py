@@ -32,9 +32,19 @@ KIND_SENTINEL = -1                     # `kinds` of the record that ends the str
 _COMMON = _KIND_BOOL << (2 * 5)        # every field an int, exp_packet a bool
 
 
+_COMMON_TYPES = (int, int, int, int, int, bool, float)
+
+
 def encode_request(request):
     """-> (values tuple for the int fields, kinds word, arrival_time) or None when a field is
     not an int / bool / None (such a request is answered in-process instead)."""
+    try:                                 # what loadGenerator.py sends: one type check for all
+        vals = (request.epoch, request.batch_id, request.batch_size, request.sub_id,
+                request.total_sub_batches, request.exp_packet, request.arrival_time)
+        if tuple(map(type, vals)) == _COMMON_TYPES:
+            return vals[:5] + (int(vals[5]),), _COMMON, vals[6]
+    except AttributeError:
+        pass
     vals, kinds = [], 0
     for i, name in enumerate(_INT_FIELDS):
         v = getattr(request, name, None)
