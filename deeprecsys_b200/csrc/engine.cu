@@ -218,6 +218,7 @@ struct drs_engine {
   int n_sm = 148;
   bool mlp_chain = true;      // fuse whole MLP stacks into one tcgen05 kernel when shapes allow
   bool tap_hidden = false;    // chain mode: also store hidden activations for drs_fetch_stage
+  bool din_fused = true;      // DIN: attention units + Sum + Concat in one kernel (narrow MLPs)
   int tc_persistent = 1;      // k_fc_tc_persist: 0 never, 1 for grids of more than one wave,
                               // n >= 2 always, with at most n CTAs
 
@@ -946,7 +947,26 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
       TRY(launch_gather(e, ln, s, B, false, pk));
       PROF_MARK(2);
       TRY(exchange_after_gather(e, ln, rows));
-      if (rows > 0) {
+      // one fused kernel when the attention MLP is narrow enough to live in a warp
+      bool fused = e->din_fused && D <= 32 && (int)e->bot.layers.size() <= kDinMaxLayers;
+      for (const Layer& l : e->bot.layers) fused = fused && l.out <= 32;
+      if (rows > 0 && fused) {
+        DinAttnParams q{};
+        q.P = ln.P; q.ldp = ldp; q.R = ln.R; q.ldr = e->ld_R;
+        q.rows = rows; q.D = D; q.T = T; q.n_units = nu;
+        q.n_layers = (int)e->bot.layers.size();
+        q.width[0] = 3 * D;
+        for (int i = 0; i < q.n_layers; ++i) {
+          q.width[i + 1] = e->bot.layers[i].out;
+          q.W[i] = e->bot.layers[i].W;
+          q.b[i] = e->bot.layers[i].b;
+        }
+        int grid = ceil_div(rows, 256 / kWarp);
+        if (grid > e->n_sm * 8) grid = e->n_sm * 8;
+        k_din_attention<<<grid, 256, 0, ln.stream>>>(q);
+        CU(cudaGetLastError());
+        e->launches += 1;
+      } else if (rows > 0) {
         k_din_concat<<<ew_grid((int64_t)nu * rows * D), 256, 0, ln.stream>>>(
             ln.P, ldp, ln.C, cap * 3 * D, rows, D, nu, T - 2);
         CU(cudaGetLastError());
@@ -2198,6 +2218,7 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   else if (k == "tap_hidden") e->tap_hidden = value != 0;
   else if (k == "cuda_graphs") e->use_graphs = value != 0;
   else if (k == "tc_persistent") e->tc_persistent = (int)value;
+  else if (k == "din_fused") e->din_fused = value != 0;
   else if (k == "exchange") {
     CHECK_ARG(value == 0 || value == 1, "exchange must be 0 (fused peer stores) or 1 (unfused)");
     CHECK_ARG(!e->row_mode, "the unfused exchange baseline is table-wise");

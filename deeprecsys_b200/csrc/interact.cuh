@@ -85,6 +85,97 @@ __global__ void k_unpack_exchange(const float* __restrict__ recv, int S, int tpr
   }
 }
 
+// ---------------------------------------------------------------- fused DIN attention
+// din.py:246-331 for one sample per warp, all behaviour tables in one pass over the pooled
+// vectors: for every unit u (own weights each)
+//     c   = Concat(e_u, e_ad, Sum(e_u, e_ad))                    [3D]     din.py:263-273
+//     o_u = MLP_u(c), layers [3D] + arch_mlp_bot + [D], all ReLU           :253-258, :278
+// atten = Sum_u o_u (left to right, :283), and the top-MLP input
+//     R = Concat(e_profile, atten, e_ad, e_ctx)                  [4D]     :319-325
+// Replaces k_din_concat + n_layers batched FC launches + k_sum_units + three k_copy_cols and the
+// [n_units, B, 3D] / [n_units, B, h] intermediates they pass through HBM (DIN with 251 behaviour
+// tables: ~1.3 GB per 4,096 samples) by one read of the pooled vectors.
+// Lane j owns column j (D <= 32).  Layer 0 is a distributed dot product (each lane multiplies
+// its three elements of c, warp-reduced: fp32 reassociation only); narrower layers keep their
+// activations one per lane and broadcast them by shuffle.  Hidden widths <= 32.
+constexpr int kDinMaxLayers = 4;
+constexpr int kDinPrefetch = 8;             // units whose e_u load is in flight per sample
+struct DinAttnParams {
+  const float* P;  int64_t ldp;             // pooled [rows, T*D]
+  float* R;  int64_t ldr;                   // top-MLP input [rows, 4*D]
+  int rows, D, T, n_units, n_layers;
+  int width[kDinMaxLayers + 1];             // 3D, hidden..., D
+  const float* W[kDinMaxLayers];            // [n_units][out][in]
+  const float* b[kDinMaxLayers];            // [n_units][out]
+};
+
+__global__ void __launch_bounds__(256) k_din_attention(const DinAttnParams p) {
+  const int lane = threadIdx.x % kWarp;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+  const int nwarps = (gridDim.x * blockDim.x) / kWarp;
+  const int D = p.D, nl = p.n_layers;
+  const bool col = lane < D;
+  for (int s = warp; s < p.rows; s += nwarps) {
+    const float* prow = p.P + (int64_t)s * p.ldp;
+    const float ead = col ? __ldg(prow + (int64_t)(p.T - 2) * D + lane) : 0.f;
+    float atten = 0.f;
+    float pre[kDinPrefetch];
+#pragma unroll
+    for (int i = 0; i < kDinPrefetch; ++i)
+      pre[i] = (col && i < p.n_units) ? __ldg(prow + (int64_t)(1 + i) * D + lane) : 0.f;
+    for (int u0 = 0; u0 < p.n_units; u0 += kDinPrefetch) {
+#pragma unroll
+      for (int i = 0; i < kDinPrefetch; ++i) {
+        const int u = u0 + i;
+        if (u >= p.n_units) break;
+        const float eu = pre[i];
+        const int un = u + kDinPrefetch;
+        pre[i] = (col && un < p.n_units) ? __ldg(prow + (int64_t)(1 + un) * D + lane) : 0.f;
+        const float c2 = eu + ead;
+        // layer 0: [3D] -> width[1]; lane k ends up holding activation k
+        float act = 0.f;
+        {
+          const int out = p.width[1], in = p.width[0];
+          const float* W = p.W[0] + (int64_t)u * out * in;
+          const float* b = p.b[0] + (int64_t)u * out;
+          for (int k = 0; k < out; ++k) {
+            float part = 0.f;
+            if (col) {
+              const float* w = W + (int64_t)k * in;
+              part = fmaf(__ldg(w + lane), eu, part);
+              part = fmaf(__ldg(w + D + lane), ead, part);
+              part = fmaf(__ldg(w + 2 * D + lane), c2, part);
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const float a = fmaxf(part + __ldg(b + k), 0.f);
+            if (lane == k) act = a;
+          }
+        }
+        // layers 1 .. nl-1: lane j computes output j from the broadcast activations
+        for (int l = 1; l < nl; ++l) {
+          const int in = p.width[l], out = p.width[l + 1];
+          const float* W = p.W[l] + (int64_t)u * out * in;
+          float acc = lane < out ? __ldg(p.b[l] + (int64_t)u * out + lane) : 0.f;
+          for (int k = 0; k < in; ++k) {
+            const float ak = __shfl_sync(0xffffffffu, act, k);
+            if (lane < out) acc = fmaf(__ldg(W + (int64_t)lane * in + k), ak, acc);
+          }
+          act = lane < out ? fmaxf(acc, 0.f) : 0.f;
+        }
+        atten += act;                        // Sum over units, in unit order
+      }
+    }
+    if (col) {
+      float* r = p.R + (int64_t)s * p.ldr;
+      r[lane] = __ldg(prow + lane);                                   // user profile (table 0)
+      r[D + lane] = atten;
+      r[2 * D + lane] = ead;                                          // candidate ad (table T-2)
+      r[3 * D + lane] = __ldg(prow + (int64_t)(p.T - 1) * D + lane);  // context (table T-1)
+    }
+  }
+}
+
 constexpr int kStackMaxSrc = 32;
 struct StackRows {
   int n;                                  // requests

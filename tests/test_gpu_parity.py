@@ -228,3 +228,28 @@ def test_persistent_tensor_core_fc_many_tiles_per_cta(name, ctas, precision, ato
         eng.set_option("tc_persistent", 0)             # one CTA per tile: same numbers
         out0, _ = eng.infer(dense, ids, lengths, B)
         assert np.array_equal(out.view(np.uint32), out0.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["din", "din_many", "din254"])
+def test_fused_din_attention_equals_the_unfused_graph(name):
+    """k_din_attention (attention units + Sum + Concat in one pass over the pooled vectors)
+    against the per-layer graph it replaces (k_din_concat -> batched FCs -> k_sum_units ->
+    copies) and against the oracle, ragged batch sizes included."""
+    c = make_case(name, num_batches=1, max_batch=64)
+    with AccelEngine(args=c.args, max_batch=64) as eng:
+        eng.load_parameters(c.tables, c.fcs)
+        for B in (64, 33, 1):
+            dense, ids, lengths = request(c, 0, B)
+            st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+            eng.set_option("din_fused", 1)
+            out_f, _ = eng.infer(dense, ids, lengths, B)
+            att_f = eng.fetch_stage(_lib.STAGE_BOT)
+            inter_f = eng.fetch_stage(_lib.STAGE_INTERACT)
+            eng.set_option("din_fused", 0)
+            out_u, _ = eng.infer(dense, ids, lengths, B)
+            att_u = eng.fetch_stage(_lib.STAGE_BOT)
+            np.testing.assert_allclose(att_f, st["bot"][0], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(att_f, att_u, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(inter_f, st["interact"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(out_f, st["out"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(out_f, out_u, rtol=1e-4, atol=1e-5)
