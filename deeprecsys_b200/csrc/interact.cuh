@@ -115,56 +115,76 @@ __global__ void __launch_bounds__(256) k_din_attention(const DinAttnParams p) {
   const int nwarps = (gridDim.x * blockDim.x) / kWarp;
   const int D = p.D, nl = p.n_layers;
   const bool col = lane < D;
+  constexpr int U = kDinPrefetch;            // units processed together (independent chains)
   for (int s = warp; s < p.rows; s += nwarps) {
     const float* prow = p.P + (int64_t)s * p.ldp;
     const float ead = col ? __ldg(prow + (int64_t)(p.T - 2) * D + lane) : 0.f;
     float atten = 0.f;
-    float pre[kDinPrefetch];
+    float pre[U];
 #pragma unroll
-    for (int i = 0; i < kDinPrefetch; ++i)
+    for (int i = 0; i < U; ++i)
       pre[i] = (col && i < p.n_units) ? __ldg(prow + (int64_t)(1 + i) * D + lane) : 0.f;
-    for (int u0 = 0; u0 < p.n_units; u0 += kDinPrefetch) {
+    for (int u0 = 0; u0 < p.n_units; u0 += U) {
+      float eu[U], act[U];
 #pragma unroll
-      for (int i = 0; i < kDinPrefetch; ++i) {
-        const int u = u0 + i;
-        if (u >= p.n_units) break;
-        const float eu = pre[i];
-        const int un = u + kDinPrefetch;
+      for (int i = 0; i < U; ++i) {
+        eu[i] = pre[i];
+        const int un = u0 + i + U;
         pre[i] = (col && un < p.n_units) ? __ldg(prow + (int64_t)(1 + un) * D + lane) : 0.f;
-        const float c2 = eu + ead;
-        // layer 0: [3D] -> width[1]; lane k ends up holding activation k
-        float act = 0.f;
-        {
-          const int out = p.width[1], in = p.width[0];
-          const float* W = p.W[0] + (int64_t)u * out * in;
-          const float* b = p.b[0] + (int64_t)u * out;
-          for (int k = 0; k < out; ++k) {
-            float part = 0.f;
-            if (col) {
-              const float* w = W + (int64_t)k * in;
-              part = fmaf(__ldg(w + lane), eu, part);
-              part = fmaf(__ldg(w + D + lane), ead, part);
-              part = fmaf(__ldg(w + 2 * D + lane), c2, part);
-            }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            const float a = fmaxf(part + __ldg(b + k), 0.f);
-            if (lane == k) act = a;
-          }
-        }
-        // layers 1 .. nl-1: lane j computes output j from the broadcast activations
-        for (int l = 1; l < nl; ++l) {
-          const int in = p.width[l], out = p.width[l + 1];
-          const float* W = p.W[l] + (int64_t)u * out * in;
-          float acc = lane < out ? __ldg(p.b[l] + (int64_t)u * out + lane) : 0.f;
-          for (int k = 0; k < in; ++k) {
-            const float ak = __shfl_sync(0xffffffffu, act, k);
-            if (lane < out) acc = fmaf(__ldg(W + (int64_t)lane * in + k), ak, acc);
-          }
-          act = lane < out ? fmaxf(acc, 0.f) : 0.f;
-        }
-        atten += act;                        // Sum over units, in unit order
+        act[i] = 0.f;
       }
+      // layer 0: [3D] -> width[1] for the U units at once; lane k ends up holding activation k
+      {
+        const int out = p.width[1], in = p.width[0];
+        for (int k = 0; k < out; ++k) {
+          float part[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const int u = min(u0 + i, p.n_units - 1);          // (clamped: result unused past the end)
+            const float* w = p.W[0] + ((int64_t)u * out + k) * in;
+            part[i] = 0.f;
+            if (col) {
+              part[i] = fmaf(__ldg(w + lane), eu[i], part[i]);
+              part[i] = fmaf(__ldg(w + D + lane), ead, part[i]);
+              part[i] = fmaf(__ldg(w + 2 * D + lane), eu[i] + ead, part[i]);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < U; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const int u = min(u0 + i, p.n_units - 1);
+            const float a = fmaxf(part[i] + __ldg(p.b[0] + (int64_t)u * out + k), 0.f);
+            if (lane == k) act[i] = a;
+          }
+        }
+      }
+      // layers 1 .. nl-1: lane j computes output j from the broadcast activations
+      for (int l = 1; l < nl; ++l) {
+        const int in = p.width[l], out = p.width[l + 1];
+        float acc[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int u = min(u0 + i, p.n_units - 1);
+          acc[i] = lane < out ? __ldg(p.b[l] + (int64_t)u * out + lane) : 0.f;
+        }
+        for (int k = 0; k < in; ++k) {
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const int u = min(u0 + i, p.n_units - 1);
+            const float ak = __shfl_sync(0xffffffffu, act[i], k);
+            if (lane < out)
+              acc[i] = fmaf(__ldg(p.W[l] + ((int64_t)u * out + lane) * in + k), ak, acc[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) act[i] = lane < out ? fmaxf(acc[i], 0.f) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i)
+        if (u0 + i < p.n_units) atten += act[i];               // Sum over units, in unit order
     }
     if (col) {
       float* r = p.R + (int64_t)s * p.ldr;
