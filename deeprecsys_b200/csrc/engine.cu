@@ -963,7 +963,8 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
         }
         int grid = ceil_div(rows, 256 / kWarp);
         if (grid > e->n_sm * 8) grid = e->n_sm * 8;
-        k_din_attention<<<grid, 256, 0, ln.stream>>>(q);
+        if (nu >= kDinPrefetch) k_din_attention<kDinPrefetch><<<grid, 256, 0, ln.stream>>>(q);
+        else k_din_attention<1><<<grid, 256, 0, ln.stream>>>(q);
         CU(cudaGetLastError());
         e->launches += 1;
       } else if (rows > 0) {

@@ -109,13 +109,15 @@ struct DinAttnParams {
   const float* b[kDinMaxLayers];            // [n_units][out]
 };
 
+// U: units processed together (independent dependency chains interleaved); 1 for models with a
+// handful of behaviour tables, kDinPrefetch for long behaviour sequences.
+template <int U>
 __global__ void __launch_bounds__(256) k_din_attention(const DinAttnParams p) {
   const int lane = threadIdx.x % kWarp;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
   const int nwarps = (gridDim.x * blockDim.x) / kWarp;
   const int D = p.D, nl = p.n_layers;
   const bool col = lane < D;
-  constexpr int U = kDinPrefetch;            // units processed together (independent chains)
   for (int s = warp; s < p.rows; s += nwarps) {
     const float* prow = p.P + (int64_t)s * p.ldp;
     const float ead = col ? __ldg(prow + (int64_t)(p.T - 2) * D + lane) : 0.f;
