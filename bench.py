@@ -19,10 +19,11 @@ Prints ONE JSON line.  Headline keys (BASELINE.json's metric on RMC1, replicas a
 Beside them, in the same line:
   secondary      (N = 1) the other BASELINE configs — rm2, rm3, wnd, ncf, din, din254 — each with
                  value / e2e / cpu_baseline / roofline (HBM GB/s or tensor TFLOP/s) / parity
-  sharded        (N > 1) the split north_star names: RMC1 table-wise, RMC1 row-wise and RMC3
-                 table-wise across the N GPUs, pooled vectors exchanged by K1's peer stores over
-                 NVLink; each leg with value / roofline / clocks and an in-bench parity check of
-                 sampled rows against the CPU oracle (outside the timed region)
+  sharded        (N > 1) the split north_star names: RMC1 table-wise (fused peer-store exchange
+                 and the unfused NCCL all-to-all baseline), RMC1 row-wise, RMC3 and RMC2
+                 table-wise across the N GPUs; each leg with value / roofline / clocks and an
+                 in-bench parity check of sampled rows against the CPU oracle (outside the timed
+                 region)
 """
 from __future__ import absolute_import, division, print_function
 
@@ -92,7 +93,7 @@ def parse_args():
                    help="comma list to restrict the secondary block, e.g. rm2,wnd")
     p.add_argument("--no_sharded", action="store_true",
                    help="N>1: skip the table-/row-sharded legs")
-    p.add_argument("--sharded", type=str, default="rm1:table,rm1:table_nccl,rm1:row,rm3:table",
+    p.add_argument("--sharded", type=str, default="rm1:table,rm1:table_nccl,rm1:row,rm3:table,rm2:table",
                    help="N>1: comma list of config:mode sharded legs")
     p.add_argument("--no_system", action="store_true",
                    help="skip the Poisson-arrival serving run through the Queue API")
@@ -889,7 +890,9 @@ def run_sharded_leg(env, opts, config, mode):
     rank's own B samples."""
     t_start = time.time()
     steps = max(5, opts.steps)
-    w = Workload(env, opts, config, int(opts.batch), 2, shard=mode)
+    # samples per GPU and step: the headline's, except RMC2 (983 KB of rows per sample)
+    B = {"rm2": min(int(opts.batch), 2048)}.get(config, int(opts.batch))
+    w = Workload(env, opts, config, B, 2, shard=mode)
     try:
         par = w.parity()
         par["ok"] = env.all_ok(par["ok"])

@@ -28,7 +28,7 @@ def main():
         return main_row(rank, world, local, precision)
     if mode == "nccl":
         return main_nccl(rank, world, local, precision)
-    for name in ("dlrm_cat", "wnd", "ncf", "din_many", "dlrm_rm3_like", "mtwnd"):
+    for name in ("dlrm_cat", "wnd", "ncf", "din_many", "dlrm_rm3_like", "mtwnd", "dlrm_rm2_like"):
         mb = 24 if name == "dlrm_rm3_like" else 96
         c = make_case(name, num_batches=2, max_batch=mb)       # same seed on every rank
         S = shard.slice_size(mb, world)

@@ -85,7 +85,7 @@ def test_two_ranks_over_gloo_run_the_sharded_legs_with_parity():
     port = str(29700 + os.getpid() % 200)
     # (the unfused NCCL-exchange leg needs real device buffers: not part of the dry run)
     procs = [_run(["--gpus", "2"] + COMMON + ["--no_e2e", "--no_sweep", "--sharded",
-                                             "rm1:table,rm1:row,rm3:table"],
+                                             "rm1:table,rm1:row,rm3:table,rm2:table"],
                   env={"RANK": str(r), "LOCAL_RANK": str(r), "WORLD_SIZE": "2",
                        "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": port}) for r in range(2)]
     outs = [_finish(p) for p in procs]
@@ -94,7 +94,7 @@ def test_two_ranks_over_gloo_run_the_sharded_legs_with_parity():
     assert d["n_gpus"] == 2 and d["config"]["parallelism"] == "replica x2"
     assert d["secondary"] is None
     legs = d["sharded"]
-    assert sorted(legs) == ["rm3_table", "row", "table"]
+    assert sorted(legs) == ["rm2_table", "rm3_table", "row", "table"]
     for key, leg in legs.items():
         assert "error" not in leg, (key, leg)
         assert leg["value"] > 0 and leg["clocks"] is not None and len(leg["parity_detail"]) == 2
