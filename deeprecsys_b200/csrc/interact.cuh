@@ -120,19 +120,21 @@ __global__ void __launch_bounds__(256) k_din_attention(const DinAttnParams p) {
   const bool col = lane < D;
   for (int s = warp; s < p.rows; s += nwarps) {
     const float* prow = p.P + (int64_t)s * p.ldp;
-    const float ead = col ? __ldg(prow + (int64_t)(p.T - 2) * D + lane) : 0.f;
+    // pooled vectors are read once: keep them out of L1, where the units' weights (re-read by
+    // every sample) should stay
+    const float ead = col ? ldg_stream_f1(prow + (int64_t)(p.T - 2) * D + lane) : 0.f;
     float atten = 0.f;
     float pre[U];
 #pragma unroll
     for (int i = 0; i < U; ++i)
-      pre[i] = (col && i < p.n_units) ? __ldg(prow + (int64_t)(1 + i) * D + lane) : 0.f;
+      pre[i] = (col && i < p.n_units) ? ldg_stream_f1(prow + (int64_t)(1 + i) * D + lane) : 0.f;
     for (int u0 = 0; u0 < p.n_units; u0 += U) {
       float eu[U], act[U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         eu[i] = pre[i];
         const int un = u0 + i + U;
-        pre[i] = (col && un < p.n_units) ? __ldg(prow + (int64_t)(1 + un) * D + lane) : 0.f;
+        pre[i] = (col && un < p.n_units) ? ldg_stream_f1(prow + (int64_t)(1 + un) * D + lane) : 0.f;
         act[i] = 0.f;
       }
       // layer 0: [3D] -> width[1] for the U units at once; lane k ends up holding activation k
