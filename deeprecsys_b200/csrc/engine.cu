@@ -41,6 +41,7 @@
 #include "mlp_chain.cuh"
 #include "mlp_tc.cuh"
 #include "rnn.cuh"
+#include "rnn_tc.cuh"
 #include "rowshard.cuh"
 #include "shard.cuh"
 #include "sls_gather.cuh"
@@ -219,6 +220,7 @@ struct drs_engine {
   bool mlp_chain = true;      // fuse whole MLP stacks into one tcgen05 kernel when shapes allow
   bool tap_hidden = false;    // chain mode: also store hidden activations for drs_fetch_stage
   bool din_fused = true;      // DIN: attention units + Sum + Concat in one kernel (narrow MLPs)
+  bool rnn_tc = true;         // DIEN: recurrence on tcgen05 (tensor-core precisions)
   int tc_persistent = 1;      // k_fc_tc_persist: 0 never, 1 for grids of more than one wave,
                               // n >= 2 always, with at most n CTAs
 
@@ -903,6 +905,24 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
                                                                        ld_last);
           e->launches += 1;
         };
+        const bool rnn_on_tc = e->rnn_tc && e->spec.precision != DRS_PREC_FP32 &&
+                               rnn_tc_supported(H, D) && rnn_tc_supported(H, H) &&
+                               e->rnn[0].layers[1].Wsplit && e->rnn[1].layers[1].Wsplit;
+        if (rnn_on_tc) {
+          // tcgen05: both products of a step into one TMEM accumulator, h_t never leaves the SM
+          const bool s3 = e->spec.precision == DRS_PREC_TF32X3;
+          int rc = rnn_tc_launch(ln.seq, D, e->rnn[0].layers[0].Wsplit, e->rnn[0].layers[1].Wsplit,
+                                 e->rnn[0].layers[0].b, e->rnn[0].layers[1].b, N, rows, H, D,
+                                 ln.rnn_h0, nullptr, 0, s3, ln.stream);
+          if (rc == 0)
+            rc = rnn_tc_launch(ln.rnn_h0, H, e->rnn[1].layers[0].Wsplit,
+                               e->rnn[1].layers[1].Wsplit, e->rnn[1].layers[0].b,
+                               e->rnn[1].layers[1].b, N, rows, H, H, nullptr, ln.R, e->ld_R, s3,
+                               ln.stream);
+          if (rc != 0) return fail(DRS_ERR_CUDA, "tensor-core recurrence launch failed: %s",
+                                   cudaGetErrorString((cudaError_t)rc));
+          e->launches += 2;
+        } else {
         // cell 0: i2h over all N steps at once, then the recurrence
         TRY(launch_fc(e, ln, e->rnn[0].layers[0], ln.seq, D, 0, seq_rows, ln.rnn_pre, H, 0,
                       N * rows));
@@ -912,6 +932,7 @@ int enqueue_graph(drs_engine* e, Lane& ln, const InputSet& s, int B,
                       N * rows));
         recur(e->rnn[1].layers[1], nullptr, ln.R, e->ld_R);
         CU(cudaGetLastError());
+        }
         const int cols[3] = {0, T - 2, T - 1};       // profile, candidate ad, context (dien.py:418-420)
         for (int k = 0; k < 3; ++k) {
           k_copy_cols<<<ew_grid((int64_t)rows * D), 256, 0, ln.stream>>>(
@@ -1371,7 +1392,7 @@ int drs_create(const drs_spec* spec, int device, drs_engine** out) try {
             y.loaded.assign(1, 0);
             TRYB(dev_alloc_t(e, &y.W, (size_t)y.out * y.in));
             TRYB(dev_alloc_t(e, &y.b, (size_t)y.out));
-            if (k == 0 && e->spec.precision != DRS_PREC_FP32)
+            if (e->spec.precision != DRS_PREC_FP32)      // hi / lo parts for the tensor-core paths
               TRYB(dev_alloc_t(e, &y.Wsplit, (size_t)2 * y.out * y.in));
           }
         }
@@ -2220,6 +2241,7 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   else if (k == "cuda_graphs") e->use_graphs = value != 0;
   else if (k == "tc_persistent") e->tc_persistent = (int)value;
   else if (k == "din_fused") e->din_fused = value != 0;
+  else if (k == "rnn_tc") e->rnn_tc = value != 0;
   else if (k == "exchange") {
     CHECK_ARG(value == 0 || value == 1, "exchange must be 0 (fused peer stores) or 1 (unfused)");
     CHECK_ARG(!e->row_mode, "the unfused exchange baseline is table-wise");

@@ -253,3 +253,37 @@ def test_fused_din_attention_equals_the_unfused_graph(name):
             np.testing.assert_allclose(inter_f, st["interact"], rtol=1e-5, atol=1e-6)
             np.testing.assert_allclose(out_f, st["out"], rtol=1e-4, atol=1e-5)
             np.testing.assert_allclose(out_f, out_u, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("precision,atol", [("tf32x3", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("shape", ["small", "shipped"])
+def test_tensor_core_recurrence_matches_the_oracle_and_the_ffma_kernel(shape, precision, atol):
+    """k_rnn_tc (DIEN's two tanh cells on tcgen05: x_t.Wi^T + h_{t-1}.Wg^T into one TMEM
+    accumulator, h_t kept on the SM) against the oracle and against the FFMA recurrence it
+    replaces; 300 samples = two full 128-row tiles and a ragged one.  "shipped": D = 32, H = 64,
+    40 behaviour tables as in dien.json (small tables)."""
+    B = 300
+    extra = [] if shape == "small" else [
+        "--arch_sparse_feature_size", "32", "--hidden_size", "64",
+        "--arch_embedding_size", "300-" + "-".join(["200"] * 40) + "-400-500"]
+    c = make_case("dien", num_batches=1, max_batch=B, extra=extra)
+    with AccelEngine(args=c.args, max_batch=B, precision=precision) as eng:
+        eng.load_parameters(c.tables, c.fcs)
+        dense, ids, lengths = request(c, 0, B)
+        st = O.forward(c.spec, c.tables, c.fcs, dense, ids, lengths)
+        scale = max(1.0, float(np.abs(st["out"]).max()))
+        out_tc, _ = eng.infer(dense, ids, lengths, B)
+        h_tc = eng.fetch_stage(_lib.STAGE_BOT)
+        eng.set_option("rnn_tc", 0)
+        out_ff, _ = eng.infer(dense, ids, lengths, B)
+        h_ff = eng.fetch_stage(_lib.STAGE_BOT)
+        np.testing.assert_allclose(h_ff, st["bot"][0], rtol=0, atol=max(atol, 5e-5))
+        np.testing.assert_allclose(h_tc, st["bot"][0], rtol=0, atol=max(atol, 5e-5))
+        np.testing.assert_allclose(out_tc, st["out"], rtol=0, atol=atol * scale)
+        np.testing.assert_allclose(out_tc, out_ff, rtol=0, atol=atol * scale)
+        for n in (1, 129):                                  # other tile counts, same engine
+            eng.set_option("rnn_tc", 1)
+            d2, i2, l2 = request(c, 0, n)
+            o2, _ = eng.infer(d2, i2, l2, n)
+            want = O.forward(c.spec, c.tables, c.fcs, d2, i2, l2)["out"]
+            np.testing.assert_allclose(o2, want, rtol=0, atol=atol * scale)
