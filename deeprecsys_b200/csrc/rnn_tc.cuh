@@ -17,8 +17,13 @@
 //     hi / lo split) into the swizzled A-operand tile of the next step — the recurrence never
 //     leaves the SM; cell 0 also stores every h_t (cell 1's input), cell 1 only its last state.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 x-split +
-// epilogue (thread <-> sample row, TMEM lane quarter = warp % 4).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 x-split +
+// epilogue: thread <-> sample row (TMEM lane quarter = warp % 4), the two warps of a quarter
+// take alternate 16-column chunks.  The epilogue is the step's critical path (64 tanh per
+// row and step between two dependent MMAs), hence two warps per scheduler, biases in shared
+// memory, tanh as 1 - 2 / (exp(2x) + 1) on the SFU (absolute error ~1e-7, below the 3xTF32
+// products'), and h_t stored to HBM from its shared-memory tile in 64-byte row pieces instead of
+// 16 bytes per lane.
 // Shapes: H and Kin multiples of 16, 16 <= H <= 128.  Other shapes, and the fp32 parity mode,
 // keep the FFMA kernels of rnn.cuh.
 #pragma once
@@ -29,6 +34,14 @@ namespace drs {
 
 constexpr int kRnnTcBK = 16;                         // floats per K chunk (64-byte swizzle row)
 constexpr int kRnnTcABytes = kTcBM * kRnnTcBK * 4;   // one 128-row chunk tile (hi or lo): 8 KB
+constexpr int kRnnTcThreads = 320;
+constexpr int kRnnTcEpiWarps = 8;
+
+__device__ __forceinline__ float tanh_sfu(float x) {
+  // tanh(x) = 1 - 2 / (e^{2x} + 1); clamped so that e^{2x} stays finite
+  const float e = __expf(2.f * fminf(fmaxf(x, -15.f), 15.f));
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
 
 struct RnnTcParams {
   int N, B, H, Kin, XS;                 // steps, rows, hidden width, input width, x-ring slots
@@ -45,10 +58,10 @@ __host__ __device__ inline size_t rnn_tc_smem_bytes(int H, int Kin, int XS) {
   const size_t wg = (size_t)(H / kRnnTcBK) * 2 * H * 64;
   const size_t ht = (size_t)(H / kRnnTcBK) * 2 * kRnnTcABytes;
   const size_t xr = (size_t)XS * (Kin / kRnnTcBK) * 2 * kRnnTcABytes;
-  return wi + wg + ht + xr + 1024 /*align*/ + 256 /*barriers*/;
+  return wi + wg + ht + xr + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kRnnTcThreads, 1)
 k_rnn_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWi,
          const __grid_constant__ CUtensorMap mapWg, const RnnTcParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -68,18 +81,21 @@ k_rnn_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
   uint64_t* x_ready = x_full + 4;                           // [XS]  (XS <= 4)
   uint64_t* x_empty = x_ready + 4;                          // [XS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + 4);
+  float* sbias = reinterpret_cast<float*>(bars) + 64;       // [H] bi + bg, 256 B past the barriers
 
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   const int b0 = blockIdx.x * kTcBM;
   const uint32_t tmem_cols = H <= 32 ? 32u : (H <= 64 ? 64u : 128u);
 
+  for (int i = threadIdx.x; i < H; i += kRnnTcThreads)
+    sbias[i] = __ldg(p.bias_g + i) + __ldg(p.bias_i + i);
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     mbar_init(acc_full, 1);
-    mbar_init(h_ready, 4);
+    mbar_init(h_ready, kRnnTcEpiWarps);
     for (int s = 0; s < XS; ++s) {
       mbar_init(&x_full[s], 1);
-      mbar_init(&x_ready[s], 4);
+      mbar_init(&x_ready[s], kRnnTcEpiWarps);
       mbar_init(&x_empty[s], 1);
     }
     mbar_fence_init();
@@ -152,11 +168,11 @@ k_rnn_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       }
     }
   } else {
-    // ===== warps 2..5: split x tiles hi / lo, then per step the epilogue that produces h_t
-    const int tt = threadIdx.x - 2 * kWarp;          // 0..127
+    // ===== warps 2..9: split x tiles hi / lo, then per step the epilogue that produces h_t
+    const int tt = threadIdx.x - 2 * kWarp;          // 0..255
     const int q = warp % 4;
+    const int half = (warp - 2) / 4;                 // which 16-column chunks of the row: c16 % 2
     const int row = q * 32 + lane;                   // TMEM lane == sample row of the tile
-    const bool live = b0 + row < p.B;
     auto split_x = [&](int t) {
       const int s = t % XS, u = t / XS;
       mbar_wait(&x_full[s], (uint32_t)(u & 1));
@@ -165,8 +181,8 @@ k_rnn_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
           float4* hi = reinterpret_cast<float4*>(XR + ((size_t)s * nkx + kc) * 2 * kRnnTcABytes);
           float4* lo = hi + kRnnTcABytes / 16;
 #pragma unroll
-          for (int j = 0; j < kRnnTcABytes / 16 / 128; ++j) {
-            const int i = j * 128 + tt;
+          for (int j = 0; j < kRnnTcABytes / 16 / 256; ++j) {
+            const int i = j * 256 + tt;
             const float4 v = hi[i];
             float4 h, l;
             h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -188,63 +204,56 @@ k_rnn_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUten
       mbar_wait(acc_full, (uint32_t)(t & 1));
       tc_fence_after();
       const bool last = t == p.N - 1;
-      const int64_t grow = (int64_t)t * p.B + b0 + row;
-      for (int c0 = 0; c0 < H; c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        if (H - c0 >= 32) {
-          tmem_ld_32x32b_x32(taddr, r);
-        } else {
-          tmem_ld_32x32b_x16(taddr, r);              // H % 32 == 16: the last 16 columns
+      for (int c16 = half; c16 < nkh; c16 += 2) {     // this warp's 16-column chunks
+        const int c0 = c16 * 16;
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        float v[16];
 #pragma unroll
-          for (int j = 16; j < 32; ++j) r[j] = 0u;
+        for (int j = 0; j < 16; ++j) v[j] = tanh_sfu(__uint_as_float(r[j]) + sbias[c0 + j]);
+        if (p.last_out && last && b0 + row < p.B) {
+          float* o = p.last_out + (int64_t)(b0 + row) * p.ld_last + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = v[j];
         }
-        const int ncol = min(32, H - c0);
-        float v[32];
+        // h_t chunk -> swizzled A-operand tile of step t+1 (also the staging for the HBM store)
+        unsigned char* hi = HT + (size_t)c16 * 2 * kRnnTcABytes;
+        unsigned char* lo = hi + kRnnTcABytes;
+        if (!last || p.all_out) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = c0 + j;
-          v[j] = j < ncol ? tanhf(__uint_as_float(r[j]) + (__ldg(p.bias_g + n) + __ldg(p.bias_i + n)))
-                          : 0.f;
-        }
-        if (live) {
-          if (p.all_out) {
-            float4* o = reinterpret_cast<float4*>(p.all_out + grow * H + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (4 * j < ncol) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.last_out && last) {
-            float* o = p.last_out + (int64_t)(b0 + row) * p.ld_last + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) o[j] = v[j];
-          }
-        }
-        if (!last) {                                  // h_t -> A operand of step t+1
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {            // two 16-float chunks per 32 columns
-            if (cc * 16 >= ncol) break;
-            unsigned char* hi = HT + (size_t)((c0 >> 4) + cc) * 2 * kRnnTcABytes;
-            unsigned char* lo = hi + kRnnTcABytes;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float x0 = v[cc * 16 + 4 * c + 0], x1 = v[cc * 16 + 4 * c + 1];
-              const float x2 = v[cc * 16 + 4 * c + 2], x3 = v[cc * 16 + 4 * c + 3];
-              const uint32_t off = sw64_offset(row, c);
-              if (p.split3) {
-                float4 h, w;
-                h.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
-                h.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
-                h.z = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u);
-                h.w = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u);
-                w.x = x0 - h.x; w.y = x1 - h.y; w.z = x2 - h.z; w.w = x3 - h.w;
-                *reinterpret_cast<float4*>(hi + off) = h;
-                *reinterpret_cast<float4*>(lo + off) = w;
-              } else {
-                *reinterpret_cast<float4*>(hi + off) = make_float4(x0, x1, x2, x3);
-              }
+          for (int c = 0; c < 4; ++c) {
+            const float x0 = v[4 * c + 0], x1 = v[4 * c + 1], x2 = v[4 * c + 2], x3 = v[4 * c + 3];
+            const uint32_t off = sw64_offset(row, c);
+            if (p.split3) {
+              float4 h, w;
+              h.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+              h.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+              h.z = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u);
+              h.w = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u);
+              w.x = x0 - h.x; w.y = x1 - h.y; w.z = x2 - h.z; w.w = x3 - h.w;
+              *reinterpret_cast<float4*>(hi + off) = h;
+              *reinterpret_cast<float4*>(lo + off) = w;
+            } else {
+              *reinterpret_cast<float4*>(hi + off) = make_float4(x0, x1, x2, x3);
             }
+          }
+        }
+        if (p.all_out) {
+          // every h_t to HBM (cell 1's input): read this warp's 32 rows x 64 bytes back from
+          // the tile, 4 lanes per row piece -> full 32-byte sectors, 8 row pieces per request
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = q * 32 + it * 8 + (lane >> 2), c = lane & 3;
+            const uint32_t off = sw64_offset(rr, c);
+            float4 x = *reinterpret_cast<const float4*>(hi + off);
+            if (p.split3) {
+              const float4 y = *reinterpret_cast<const float4*>(lo + off);
+              x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;       // hi + lo == h exactly
+            }
+            if (b0 + rr < p.B)
+              *reinterpret_cast<float4*>(p.all_out + ((int64_t)t * p.B + b0 + rr) * H + c0 +
+                                         4 * c) = x;
           }
         }
       }
@@ -295,8 +304,8 @@ inline int rnn_tc_launch(const float* X, int64_t ldx, const float* Wi_split, con
                                          220 * 1024);
     if (e != cudaSuccess) return (int)e;
   }
-  k_rnn_tc<<<ceil_div(B, kTcBM), kTcThreads, rnn_tc_smem_bytes(H, Kin, p.XS), stream>>>(mx, mwi,
-                                                                                       mwg, p);
+  k_rnn_tc<<<ceil_div(B, kTcBM), kRnnTcThreads, rnn_tc_smem_bytes(H, Kin, p.XS), stream>>>(
+      mx, mwi, mwg, p);
   return (int)cudaGetLastError();
 }
 
