@@ -17,7 +17,7 @@ Prints ONE JSON line.  Headline keys (BASELINE.json's metric on RMC1, replicas a
   cpu_baseline   torch-CPU port of the reference's CPU engine on this box's host cores
   system         the metric's "at p99" half: accelInferenceEngine behind multiprocessing Queues
 Beside them, in the same line:
-  secondary      (N = 1) the other BASELINE configs — rm2, rm3, wnd, ncf, din, din254 — each with
+  secondary      (N = 1) the other configs — rm2, rm3, wnd, ncf, din, din254, mtwnd, dien — each with
                  value / e2e / cpu_baseline / roofline (HBM GB/s or tensor TFLOP/s) / parity
   sharded        (N > 1) the split north_star names: RMC1 table-wise (fused peer-store exchange
                  and the unfused NCCL all-to-all baseline), RMC1 row-wise, RMC3 and RMC2
@@ -56,7 +56,7 @@ DIN254_ARGV = ["--model_type", "din", "--model_name", "din",
                "--num_indices_per_lookup", "3", "--num_indices_per_lookup_fixed", "True"]
 # samples per step of the secondary configs (sized so that one step is 0.1 - 1 ms of GPU work)
 SECONDARY = [("rm2", 4096), ("rm3", 16384), ("wnd", 16384), ("ncf", 16384), ("din", 16384),
-             ("din254", 4096)]
+             ("din254", 4096), ("mtwnd", 16384), ("dien", 16384)]
 ROOFLINE_KIND = {"rm1": "hbm", "rm2": "hbm", "rm3": "tensor", "wnd": "tensor", "ncf": "tensor",
                  "mtwnd": "tensor", "din": "latency", "din254": "hbm", "dien": "latency"}
 METRIC = "DLRM-RMC1 inferences/sec"
@@ -88,7 +88,7 @@ def parse_args():
     p.add_argument("--no_sweep", action="store_true")
     p.add_argument("--no_e2e", action="store_true")
     p.add_argument("--no_secondary", action="store_true",
-                   help="N=1: skip the rm2 / rm3 / wnd / ncf / din / din254 block")
+                   help="N=1: skip the rm2 / rm3 / wnd / ncf / din / din254 / mtwnd / dien block")
     p.add_argument("--secondary", type=str, default=None,
                    help="comma list to restrict the secondary block, e.g. rm2,wnd")
     p.add_argument("--no_sharded", action="store_true",

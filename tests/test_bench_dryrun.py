@@ -62,11 +62,13 @@ def test_single_gpu_line_carries_every_secondary_config():
     assert d["parity"]["ok"] and d["parity"]["pooled"] == "bit-exact"
     assert d["sharded"] is None
     sec = d["secondary"]
-    assert sorted(sec) == ["din", "din254", "ncf", "rm2", "rm3", "wnd"]
+    assert sorted(sec) == ["dien", "din", "din254", "mtwnd", "ncf", "rm2", "rm3", "wnd"]
     for name, s in sec.items():
         assert "error" not in s, (name, s)
         assert s["value"] > 0 and s["e2e"]["value"] > 0 and s["cpu_baseline"]["value"] > 0
-        assert s["parity"]["ok"] and s["parity"]["pooled"] == "bit-exact", (name, s["parity"])
+        assert s["parity"]["ok"], (name, s["parity"])
+        # (DIEN's Reshape mixes the samples of a batch: no per-sample parity there, tests/ has it)
+        assert s["parity"]["pooled"] == ("skipped" if name == "dien" else "bit-exact"), name
         assert s["roofline"]["bound"] in ("hbm", "tensor") and s["roofline"]["frac"] > 0
     assert sec["rm3"]["roofline"]["unit"] == "TFLOP/s" and sec["rm2"]["roofline"]["unit"] == "GB/s"
     assert "254 tables" in sec["din254"]["config"]["workload"]
