@@ -134,6 +134,7 @@ struct InputSet {                 // one query's inputs in HBM
   ScanTableDesc* scan = nullptr;  // [T] device
   std::vector<int64_t> idx_pos;   // per table start (ints, multiple of 4)
   std::vector<int64_t> idx_cap;   // per table capacity (ints)
+  int fixed_L = 0;                // > 0: every segment of every table has exactly this many ids
   int n = 0;                      // samples capacity / staged count
   int dense_rows = 0;             // rows in `dense`
   int64_t dense_row0 = 0;         // global sample index of dense row 0 (sharded: slice start)
@@ -219,6 +220,7 @@ struct drs_engine {
   int n_sm = 148;
   bool mlp_chain = true;      // fuse whole MLP stacks into one tcgen05 kernel when shapes allow
   bool tap_hidden = false;    // chain mode: also store hidden activations for drs_fetch_stage
+  bool short_fixed = true;    // fixed-length short segments take k_sls_fixed (no offsets/tiles)
   bool din_fused = true;      // DIN: attention units + Sum + Concat in one kernel (narrow MLPs)
   bool rnn_tc = true;         // DIEN: recurrence on tcgen05 (tensor-core precisions)
   int tc_persistent = 1;      // k_fc_tc_persist: 0 never, 1 for grids of more than one wave,
@@ -664,6 +666,31 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot,
     if (p.T == 0) TRY(shard_signal(e, ln, 0, ln.epoch));
   }
   if (p.T == 0) return DRS_OK;
+  // fixed-length short segments: the flat (table, 32 samples) kernel, no offsets, no tiles
+  if (e->short_fixed && !pk && !dot && s.fixed_L > 0 && s.fixed_L <= kFixedMaxL &&
+      (e->lpr == 4 || e->lpr == 8 || e->lpr == 16 || e->lpr == 32) && p.vec_store) {
+    const size_t smem = (size_t)p.T * sizeof(SlsTableDesc);
+    const int64_t items = (int64_t)ceil_div(B, 32) * p.T;
+    int64_t g = ceil_div64(items, kSlsThreads / kWarp);
+    if (g > (int64_t)e->n_sm * 8) g = (int64_t)e->n_sm * 8;
+#define DRS_FIXED_L(LPR_)                                                                 \
+    switch (s.fixed_L) {                                                                  \
+      case 1:  k_sls_fixed<LPR_, 1><<<(int)g, kSlsThreads, smem, ln.stream>>>(p); break;  \
+      case 2:  k_sls_fixed<LPR_, 2><<<(int)g, kSlsThreads, smem, ln.stream>>>(p); break;  \
+      case 3:  k_sls_fixed<LPR_, 3><<<(int)g, kSlsThreads, smem, ln.stream>>>(p); break;  \
+      default: k_sls_fixed<LPR_, 4><<<(int)g, kSlsThreads, smem, ln.stream>>>(p); break;  \
+    }
+    switch (e->lpr) {
+      case 4:  DRS_FIXED_L(4) break;
+      case 8:  DRS_FIXED_L(8) break;
+      case 16: DRS_FIXED_L(16) break;
+      default: DRS_FIXED_L(32) break;
+    }
+#undef DRS_FIXED_L
+    CU(cudaGetLastError());
+    e->launches += 1;
+    return DRS_OK;
+  }
   int grid = pk ? pk->tile_off[pk->n] : ceil_div(B, e->SB);
   // persistent path: vectorised rows, no dot fusion, offsets fit the per-thread registers
   if (persistent_gather_ok(e, dot)) {
@@ -1084,17 +1111,20 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
   int32_t* const dst_len = row ? s.lengths_raw : s.lengths;
   std::vector<int64_t>& n_idx = *n_idx_out;
   n_idx.assign(T, 0);
+  int fixed = (B > 0 && T > 0) ? lengths[0][0] : 0;       // stays > 0 while every length equals it
   for (int t = 0; t < T; ++t) {
     const int32_t* len = lengths[t];
     int64_t tot = 0;
     for (int b = 0; b < B; ++b) {
       if (len[b] < 0) return fail(DRS_ERR_INDEX, "negative length at table %d sample %d", t, b);
+      if (len[b] != fixed) fixed = 0;
       tot += len[b];
     }
     CHECK_ARG(tot <= s.idx_cap[t], "table %d: %lld lookups exceed capacity %lld", t,
               (long long)tot, (long long)s.idx_cap[t]);
     n_idx[t] = tot;
   }
+  s.fixed_L = (fixed > 0 && !(e->row_mode && e->world > 1)) ? fixed : 0;   // (row mode re-buckets)
   // lengths: one strided copy when the caller's rows are equally spaced
   bool len_strided = T > 1;
   const ptrdiff_t lstride = T > 1 ? (const char*)lengths[1] - (const char*)lengths[0] : 0;
@@ -2242,6 +2272,7 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   else if (k == "tc_persistent") e->tc_persistent = (int)value;
   else if (k == "din_fused") e->din_fused = value != 0;
   else if (k == "rnn_tc") e->rnn_tc = value != 0;
+  else if (k == "short_fixed") e->short_fixed = value != 0;
   else if (k == "exchange") {
     CHECK_ARG(value == 0 || value == 1, "exchange must be 0 (fused peer stores) or 1 (unfused)");
     CHECK_ARG(!e->row_mode, "the unfused exchange baseline is table-wise");

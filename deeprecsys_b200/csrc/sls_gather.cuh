@@ -595,6 +595,90 @@ __global__ void __launch_bounds__(kSlsThreads) k_sls_gather_persist(const SlsLau
   sls_shard_tail(p);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fixed-length short segments (Wide&Deep, NCF, DIN, DIEN, MT-WnD: every (sample, table) segment
+// has the same 1..4 lookups — the reference's request slicing REQUIRES fixed L,
+// inferenceEngine.py:204-206).  With L known the offsets are b*L: no offset arrays to stage, and
+// the ids of 32 consecutive samples of one table are one contiguous span.  One warp takes work
+// items (table t, 32 samples), t fastest, so that at any instant the chip reads many tables at
+// once while every warp's id loads and pooled-vector stores are coalesced; the tile machinery of
+// the persistent kernel (per-tile offsets from T arrays, T tiny TMA copies — all of a tile's cost
+// when a tile is one 254-table sample) is not needed.  In-segment adds stay in index order.
+constexpr int kFixedMaxL = 4;
+
+// L: lookups per segment (compile time: the in-flight rows live in registers);
+// a lane group keeps kFixedSeg segments = kFixedSeg * L row loads in flight
+template <int LPR, int L>
+__global__ void __launch_bounds__(kSlsThreads) k_sls_fixed(const SlsLaunch p) {
+  constexpr int kFixedSeg = (L == 1 && LPR <= 8) ? 8 : 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SlsTableDesc* sdesc = reinterpret_cast<SlsTableDesc*>(smem_raw);
+  for (int i = threadIdx.x; i < p.T * (int)(sizeof(SlsTableDesc) / 8); i += kSlsThreads)
+    reinterpret_cast<uint64_t*>(sdesc)[i] = reinterpret_cast<const uint64_t*>(p.tables)[i];
+  __syncthreads();
+  constexpr int G = kWarp / LPR;                        // lane groups (segments) per warp pass
+  constexpr int SPW = 32;                               // samples per work item
+  const int lane = threadIdx.x % kWarp;
+  const int gi = lane / LPR, l = lane % LPR;
+  const int warp = (blockIdx.x * kSlsThreads + threadIdx.x) / kWarp;
+  const int nwarps = (gridDim.x * kSlsThreads) / kWarp;
+  const int nblk = (p.B + SPW - 1) / SPW;
+  const int64_t items = (int64_t)nblk * p.T;
+  for (int64_t item = warp; item < items; item += nwarps) {
+    const int t = (int)(item % p.T);
+    const int b0 = (int)(item / p.T) * SPW;
+    const SlsTableDesc& td = sdesc[t];
+    const int nsamp = min(SPW, p.B - b0);
+    // the item's ids: nsamp * L consecutive ints, loaded coalesced (<= kFixedMaxL per lane)
+    int32_t myid[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const int pos = j * kWarp + lane;
+      myid[j] = pos < nsamp * L ? __ldg(td.idx + (int64_t)b0 * L + pos) : 0;
+    }
+    const float* rows_lane = td.rows + l * 4;
+    for (int s0 = gi * (SPW / G); s0 < (gi + 1) * (SPW / G); s0 += kFixedSeg) {
+      float4 v[kFixedSeg][L];
+#pragma unroll
+      for (int u = 0; u < kFixedSeg; ++u) {
+#pragma unroll
+        for (int r = 0; r < L; ++r) {                    // row r of segment s0 + u
+          v[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int pos = (s0 + u) * L + r;              // position in the item's id span
+          int32_t id = 0;
+#pragma unroll
+          for (int j = 0; j < L; ++j) {                  // the shuffle is executed by every lane
+            const int32_t c = __shfl_sync(0xffffffffu, myid[j], pos & (kWarp - 1));
+            if ((pos >> 5) == j) id = c;
+          }
+          if (s0 + u < nsamp) {
+            if ((uint32_t)id < (uint32_t)td.n_rows) v[u][r] = ldg_stream_f4(rows_lane + (int64_t)id * p.D);
+            else *p.err_flag = 1;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kFixedSeg; ++u) {
+        if (s0 + u >= nsamp) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < L; ++r) {
+          acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w;
+        }
+        const int64_t b = b0 + s0 + u;
+        float* o = (p.shard_S > 0 ? p.peer_out[b / p.shard_S] + (b % p.shard_S) * p.ld_out
+                                  : p.out + b * p.ld_out) + td.dst_col + l * 4;
+        if (p.vec_store) {
+          *reinterpret_cast<float4*>(o) = acc;
+        } else {
+          o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+        }
+      }
+    }
+  }
+  sls_shard_tail(p);
+}
+
 // lengths -> offsets (exclusive prefix sum), one CTA per table; also checks
 // Caffe2's enforce  sum(lengths) == len(indices)  when n_idx >= 0.
 // Integer-exact by construction (int32 adds in any grouping are associative).
