@@ -137,6 +137,46 @@ __global__ void __launch_bounds__(256) k_din_attention(const DinAttnParams p) {
         pre[i] = (col && un < p.n_units) ? ldg_stream_f1(prow + (int64_t)(1 + un) * D + lane) : 0.f;
         act[i] = 0.f;
       }
+      if (nl == 2) {
+        // the shipped shape [3D, h, D] (din.json: h = 1): per-unit pointers once, 32-bit offsets
+        const int h = p.width[1];
+        const float* w0[U]; const float* w1[U]; const float* bb0[U];
+        float acc[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int u = min(u0 + i, p.n_units - 1);
+          w0[i] = p.W[0] + (int64_t)u * h * (3 * D) + lane;
+          bb0[i] = p.b[0] + (int64_t)u * h;
+          w1[i] = p.W[1] + ((int64_t)u * D + lane) * h;
+          acc[i] = col ? __ldg(p.b[1] + (int64_t)u * D + lane) : 0.f;
+        }
+        for (int k = 0; k < h; ++k) {
+          float part[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            part[i] = 0.f;
+            if (col) {
+              const float* w = w0[i] + k * 3 * D;
+              part[i] = fmaf(__ldg(w), eu[i], part[i]);
+              part[i] = fmaf(__ldg(w + D), ead, part[i]);
+              part[i] = fmaf(__ldg(w + 2 * D), eu[i] + ead, part[i]);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < U; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+#pragma unroll
+          for (int i = 0; i < U; ++i) {          // every lane holds the hidden activation k
+            const float a = fmaxf(part[i] + __ldg(bb0[i] + k), 0.f);
+            if (col) acc[i] = fmaf(__ldg(w1[i] + k), a, acc[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i)
+          if (u0 + i < p.n_units) atten += fmaxf(acc[i], 0.f);     // Sum over units, in unit order
+        continue;
+      }
       // layer 0: [3D] -> width[1] for the U units at once; lane k ends up holding activation k
       {
         const int out = p.width[1], in = p.width[0];
