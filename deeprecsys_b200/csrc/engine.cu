@@ -668,7 +668,8 @@ int launch_gather(drs_engine* e, Lane& ln, const InputSet& s, int B, bool dot,
   if (p.T == 0) return DRS_OK;
   // fixed-length short segments: the flat (table, 32 samples) kernel, no offsets, no tiles
   if (e->short_fixed && !pk && !dot && s.fixed_L > 0 && s.fixed_L <= kFixedMaxL &&
-      (e->lpr == 4 || e->lpr == 8 || e->lpr == 16 || e->lpr == 32) && p.vec_store) {
+      (e->lpr == 4 || e->lpr == 8 || e->lpr == 16 || e->lpr == 32) && p.vec_store &&
+      (size_t)p.T * sizeof(SlsTableDesc) <= 40 * 1024) {
     const size_t smem = (size_t)p.T * sizeof(SlsTableDesc);
     const int64_t items = (int64_t)ceil_div(B, 32) * p.T;
     int64_t g = ceil_div64(items, kSlsThreads / kWarp);

@@ -232,7 +232,13 @@ int drs_hbm_bytes(const drs_engine* e, int64_t* bytes_allocated);
  * the unfused exchange baseline of drs_exchange_begin / drs_exchange_end.  "tc_persistent"
  * (default 1): wide FC layers whose tile grid exceeds one wave run the persistent tcgen05 kernel
  * (two TMEM accumulators, epilogue of tile i under the MMAs of tile i+1); 0 = one CTA per tile,
- * n >= 2 = always persistent with at most n CTAs. */
+ * n >= 2 = always persistent with at most n CTAs.  "short_fixed" (default 1): queries whose
+ * segments all have the same 1..4 lookups (the reference's request slicing requires fixed L) are
+ * gathered by the flat fixed-length kernel instead of the tiled one.  "din_fused" (default 1): DIN's
+ * attention units, their Sum and the Concat into the top-MLP input run as one kernel when the
+ * attention MLP's widths are <= 32.  "rnn_tc" (default 1): DIEN's recurrent cells run on tcgen05
+ * in the tensor-core precisions (H and D multiples of 16).  Setting any of the last three to 0
+ * selects the per-operator graph they replace (same values within the stated tolerances). */
 int drs_set_option(drs_engine* e, const char* key, int64_t value);
 
 /* Per-segment CUDA-event profiling of the served graph, on the engine stream:
