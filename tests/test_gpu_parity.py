@@ -290,3 +290,43 @@ def test_tensor_core_recurrence_matches_the_oracle_and_the_ffma_kernel(shape, pr
             o2, _ = eng.infer(d2, i2, l2, n)
             want = O.forward(c.spec, c.tables, c.fcs, d2, i2, l2)["out"]
             np.testing.assert_allclose(o2, want, rtol=0, atol=atol * scale)
+
+
+@pytest.mark.parametrize("name", ["wnd", "ncf", "din", "din254", "mtwnd", "dien"])
+def test_fixed_length_gather_equals_the_tiled_gather(name):
+    """k_sls_fixed (flat (table, 32 samples) work items, no offsets) against the tiled persistent
+    kernel it replaces for fixed-length short segments: pooled vectors bit for bit, staged and
+    host path, ragged batch sizes; and a query with ONE different length falls back to the tiled
+    kernel and still matches the oracle."""
+    c = make_case(name, num_batches=1, max_batch=200)
+    with AccelEngine(args=c.args, max_batch=200) as eng:
+        eng.load_parameters(c.tables, c.fcs)
+        dense, ids, lengths = request(c, 0, 200)
+        eng.stage_batch(0, dense, ids, lengths)
+        for B in (200, 97, 32, 1):
+            got = {}
+            for flag in (1, 0):
+                eng.set_option("short_fixed", flag)
+                out_s, _ = eng.infer_staged(0, B)
+                pooled_s = eng.fetch_stage(_lib.STAGE_POOLED)
+                d, i, l = request(c, 0, B)
+                out_h, _ = eng.infer(d, i, l, B)
+                pooled_h = eng.fetch_stage(_lib.STAGE_POOLED)
+                assert np.array_equal(pooled_s.view(np.uint32), pooled_h.view(np.uint32))
+                got[flag] = (pooled_s, out_s)
+            assert np.array_equal(got[1][0].view(np.uint32), got[0][0].view(np.uint32))
+            if name != "dien":                   # (DIEN's reshape needs the whole batch)
+                st = O.forward(c.spec, c.tables, c.fcs, *request(c, 0, B))
+                assert np.array_equal(got[1][0].view(np.uint32), st["pooled"].view(np.uint32))
+        if name == "wnd":                        # one shorter segment: not fixed-length any more
+            eng.set_option("short_fixed", 1)
+            d, i, l = request(c, 0, 64)
+            l = [x.copy() for x in l]
+            i = [x.copy() for x in i]
+            l[3][10] = 0
+            i[3] = np.delete(i[3], 10)
+            out, _ = eng.infer(d, i, l, 64)
+            st = O.forward(c.spec, c.tables, c.fcs, d, i, l)
+            assert np.array_equal(eng.fetch_stage(_lib.STAGE_POOLED).view(np.uint32),
+                                  st["pooled"].view(np.uint32))
+            np.testing.assert_allclose(out, st["out"], rtol=1e-4, atol=1e-5)
