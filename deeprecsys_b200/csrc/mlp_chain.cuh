@@ -88,8 +88,9 @@ k_mlp_chain(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
             const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
             const __grid_constant__ CUtensorMap mapW3, const ChainParams p) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic loads and stores)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* a_ring = base;                                              // slot: hi | lo
   unsigned char* b_ring = base + kChainASlots * 2 * kChainABytes;            // slot: hi | lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + kChainBSlots * 2 * kChainBBytes);

@@ -180,8 +180,9 @@ k_fc_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtens
 
   extern __shared__ unsigned char smem_dyn[];
   // 1024-B alignment required by SWIZZLE_128B
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic loads and stores)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* tiles = base;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES);
   uint64_t* full = bars;                   // TMA -> transform
@@ -356,8 +357,9 @@ k_fc_tc_persist(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;              // power of two, <= 512
 
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic loads and stores)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* tiles = base;
   float* stage_tiles = reinterpret_cast<float*>(base + (size_t)STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * STAGE_BYTES +

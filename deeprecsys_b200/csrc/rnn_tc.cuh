@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(kRnnTcThreads, 1)
 k_rnn_tc(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWi,
          const __grid_constant__ CUtensorMap mapWg, const RnnTcParams p) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the shared array, not an integer round trip: the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic loads and stores)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int H = p.H, nkx = p.Kin / kRnnTcBK, nkh = H / kRnnTcBK, XS = p.XS;
   const uint32_t wtile = (uint32_t)H * 64u;                 // one weight chunk tile (hi or lo)
   unsigned char* WI = base;                                 // [nkx][hi | lo]
