@@ -312,20 +312,6 @@ def _direct_put(q):
     return put
 
 
-def _readable_probe(q):
-    """``probe() -> bool``: is a packet waiting on this queue's pipe?  ``Queue.get(block=False)``
-    answers the same question through ``connection.wait`` (a selector object built, registered
-    and torn down per call: ~10 us of the ~50 us a packet costs the serving loop); a ``poll``
-    object registered once answers in about one.  None when the queue is not a stock Queue."""
-    try:
-        import select
-        poller = select.poll()
-        poller.register(q._reader.fileno(), select.POLLIN)
-    except (AttributeError, OSError, ValueError):
-        return None
-    return lambda: bool(poller.poll(0))
-
-
 def _die_with_parent():
     """Linux: deliver SIGTERM to this process when its parent dies (DeepRecSys.py:179 ends the
     run by terminate()-ing the engine processes; sibling GPU workers must not outlive that)."""
