@@ -78,6 +78,9 @@ _SIGNATURES = {
     "drs_sync": (C.c_int, [C.c_void_p]),
     "drs_packed_words": (C.c_int64, [C.c_int64, C.c_int]),
     "drs_pack_ids": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "drs_hostpack_words": (C.c_int64, [C.c_int64, C.c_int]),
+    "drs_hostpack_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                   C.POINTER(C.c_int)]),
     "drs_enqueue_host_packed": (C.c_int, [C.c_void_p, C.c_void_p, _PP, C.POINTER(C.c_int32), _PP,
                                           C.c_int, C.c_void_p]),
     "drs_submit_staged": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,

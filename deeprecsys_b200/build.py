@@ -17,6 +17,11 @@ LIB_PATH = os.path.join(LIB_DIR, "libdrs_b200.so")
 STAMP = LIB_PATH + ".stamp"
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
+# host-only translation units (g++: GCC vector extensions + per-ISA clones, which nvcc's front
+# end does not take); linked into the same .so
+HOST_SOURCES = ["hostpack.cpp"]
+HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-pthread"]
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -27,14 +32,14 @@ NVCC_FLAGS = [
 
 def _sources():
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
-                   if f.endswith((".cu", ".cuh", ".h")))
+                   if f.endswith((".cu", ".cuh", ".h", ".cpp")))
     files.append(os.path.join(INCLUDE, "drs_b200.h"))
     return files
 
 
 def _digest():
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + HOST_FLAGS).encode())
     for path in _sources():
         with open(path, "rb") as f:
             h.update(os.path.basename(path).encode())   # location-independent: the tree is copied
@@ -55,8 +60,19 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
+        hcmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + ["-c", os.path.join(CSRC, src),
+                                                              "-o", obj]
+        hp = subprocess.run(hcmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or hp.returncode != 0:
+            sys.stderr.write(hp.stdout)
+        if hp.returncode != 0:
+            raise RuntimeError("g++ failed (%d): %s" % (hp.returncode, " ".join(hcmd)))
+        objs.append(obj)
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-I", INCLUDE, "-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
+        "-I", INCLUDE, "-o", LIB_PATH, os.path.join(CSRC, "engine.cu")] + objs
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)

@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostpack.h"
 #include "interact.cuh"
 #include "mlp_ffma.cuh"
 #include "mlp_chain.cuh"
@@ -135,6 +136,9 @@ struct InputSet {                 // one query's inputs in HBM
   std::vector<int64_t> idx_pos;   // per table start (ints, multiple of 4)
   std::vector<int64_t> idx_cap;   // per table capacity (ints)
   int fixed_L = 0;                // > 0: every segment of every table has exactly this many ids
+  // host-packed uploads (drs_set_option "host_pack"): pinned staging for the packed blocks
+  uint32_t* pack_host = nullptr;
+  std::vector<int64_t> pack_pos;  // per table start (words) inside pack_host
   int n = 0;                      // samples capacity / staged count
   int dense_rows = 0;             // rows in `dense`
   int64_t dense_row0 = 0;         // global sample index of dense row 0 (sharded: slice start)
@@ -225,6 +229,8 @@ struct drs_engine {
   bool rnn_tc = true;         // DIEN: recurrence on tcgen05 (tensor-core precisions)
   int tc_persistent = 1;      // k_fc_tc_persist: 0 never, 1 for grids of more than one wave,
                               // n >= 2 always, with at most n CTAs
+  HostPacker* packer = nullptr;   // "host_pack" > 0: ids are bit-packed on the host before the copy
+  int64_t host_pack_min_ids = 1 << 16;   // smaller queries are uploaded as they come
 
   // gather launch geometry
   int lpr = 0, SB = 1, idx_cap = 0;
@@ -342,6 +348,7 @@ void free_input_set(InputSet& s) {
   cudaFree(s.off); cudaFree(s.descs); cudaFree(s.scan);
   cudaFree(s.idx_raw); cudaFree(s.lengths_raw); cudaFree(s.off_raw); cudaFree(s.scan_raw);
   cudaFree(s.bdescs);
+  if (s.pack_host) cudaFreeHost(s.pack_host);
   s = InputSet();
 }
 
@@ -1091,6 +1098,104 @@ Lane& pick_lane(drs_engine* e) {
   return ln;
 }
 
+// ---- host-packed id upload (drs_set_option "host_pack"; layout in hostpack.h) ----------------
+int table_id_bits(int64_t rows) {
+  int b = 1;
+  while (b < 31 && (int64_t(1) << b) < rows) ++b;
+  return b;
+}
+
+// one table's ids as the caller holds them (int32: straight copy; int64: copy + Cast kernel)
+int upload_table_plain(drs_engine* e, InputSet& s, cudaStream_t stream, const void* ids,
+                       int idx_is_i64, int64_t n, int t, int32_t* dst_idx) {
+  if (idx_is_i64) {
+    CU(cudaMemcpyAsync(s.idx64 + s.idx_pos[t], ids, (size_t)n * sizeof(int64_t),
+                       cudaMemcpyHostToDevice, stream));
+    k_cast_i64_i32<<<ew_grid(n), 256, 0, stream>>>(s.idx64 + s.idx_pos[t], dst_idx + s.idx_pos[t],
+                                                   n);
+    CU(cudaGetLastError());
+    e->launches += 1;
+  } else {
+    CU(cudaMemcpyAsync(dst_idx + s.idx_pos[t], ids, (size_t)n * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, stream));
+  }
+  return DRS_OK;
+}
+
+int ensure_pack_staging(drs_engine* e, InputSet& s) {
+  if (s.pack_host || !s.idx64) return DRS_OK;
+  s.pack_pos.assign(e->T + 1, 0);
+  for (int t = 0; t < e->T; ++t)
+    s.pack_pos[t + 1] = s.pack_pos[t] +
+                        pack_block_words(s.idx_cap[t], table_id_bits(e->table_rows[t]));
+  CU(cudaHostAlloc((void**)&s.pack_host, (size_t)std::max<int64_t>(16, s.pack_pos[e->T]) * 4,
+                   cudaHostAllocDefault));
+  return DRS_OK;
+}
+
+struct PackUpload {
+  drs_engine* e; InputSet* s; cudaStream_t stream; const void* const* idx; int idx_is_i64;
+  int32_t* dst_idx; std::vector<PackJob> jobs; std::vector<int> table; int rc = DRS_OK;
+};
+
+// called on the uploading thread, in table order, as soon as a table is packed: its copy goes
+// out while the pool packs the next tables
+void pack_upload_done(int j, void* ctx) {
+  PackUpload& u = *static_cast<PackUpload*>(ctx);
+  if (u.rc != DRS_OK) return;
+  const PackJob& jb = u.jobs[j];
+  const int t = u.table[j];
+  InputSet& s = *u.s;
+  if (!jb.ok) {
+    // an id that is negative or past the table: upload the caller's ids untouched so that the
+    // gather raises DRS_ERR_INDEX exactly as it does without packing
+    u.rc = upload_table_plain(u.e, s, u.stream, u.idx[t], u.idx_is_i64, jb.n, t, u.dst_idx);
+    return;
+  }
+  // the copy only: the widening kernels follow once every table is on its way, so that the
+  // copy engine runs the tables back to back (a kernel between two copies of one stream costs a
+  // copy-engine <-> SM hand-over each way)
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(s.idx64 + s.idx_pos[t]);
+  cudaError_t err = cudaMemcpyAsync(scratch, jb.out, (size_t)pack_block_words(jb.n, jb.bits) * 4,
+                                    cudaMemcpyHostToDevice, u.stream);
+  if (err != cudaSuccess) u.rc = fail(DRS_ERR_CUDA, "host-packed upload: %s", cudaGetErrorString(err));
+}
+
+int upload_ids_hostpacked(drs_engine* e, InputSet& s, cudaStream_t stream, const void* const* idx,
+                          int idx_is_i64, const std::vector<int64_t>& n_idx, int32_t* dst_idx) {
+  PackUpload u;
+  u.e = e; u.s = &s; u.stream = stream; u.idx = idx; u.idx_is_i64 = idx_is_i64; u.dst_idx = dst_idx;
+  for (int t = 0; t < e->T; ++t) {
+    if (n_idx[t] == 0 || !owns(e, t)) continue;
+    const int bits = table_id_bits(e->table_rows[t]);
+    const int64_t words = pack_block_words(n_idx[t], bits);
+    // worth packing: at least a quarter of the int32 bytes saved, and the blocks fit the scratch
+    if (bits > 24 || words * 4 > s.idx_cap[t] * 8) {
+      TRY(upload_table_plain(e, s, stream, idx[t], idx_is_i64, n_idx[t], t, dst_idx));
+      continue;
+    }
+    PackJob jb;
+    jb.ids = idx[t]; jb.is_i64 = idx_is_i64; jb.n = n_idx[t]; jb.bits = bits;
+    jb.out = s.pack_host + s.pack_pos[t];
+    u.jobs.push_back(jb);
+    u.table.push_back(t);
+  }
+  if (!u.jobs.empty())
+    hostpack_run(e->packer, u.jobs.data(), (int)u.jobs.size(), pack_upload_done, &u);
+  TRY(u.rc);
+  for (size_t j = 0; j < u.jobs.size(); ++j) {
+    const PackJob& jb = u.jobs[j];
+    if (!jb.ok) continue;                      // went up unpacked
+    const int t = u.table[j];
+    k_unpack_ids_blk<<<ew_grid(jb.n), 256, 0, stream>>>(
+        reinterpret_cast<const uint32_t*>(s.idx64 + s.idx_pos[t]), jb.bits, jb.n,
+        dst_idx + s.idx_pos[t]);
+    CU(cudaGetLastError());
+    e->launches += 1;
+  }
+  return DRS_OK;
+}
+
 // upload one query into an InputSet (host -> device on `stream`).  Sharded: ids are uploaded
 // only for owned tables (lengths and dense rows for all: they are small).
 // pack_bits != nullptr: idx[t] is a packed stream of pack_bits[t]-bit ids (drs_pack_ids)
@@ -1138,6 +1243,14 @@ int upload_inputs(drs_engine* e, InputSet& s, cudaStream_t stream, const float* 
     for (int t = 0; t < T; ++t)
       CU(cudaMemcpyAsync(dst_len + (size_t)t * s.n, lengths[t], (size_t)B * sizeof(int32_t),
                          cudaMemcpyHostToDevice, stream));
+  }
+  // "host_pack": the caller's int32/int64 ids are bit-packed by the engine's host threads into
+  // the slot's pinned staging, table by table, each table's copy leaving as soon as it is packed
+  if (!pack_bits && e->packer && s.pack_host && (e->world == 1 || row)) {
+    int64_t total = 0;
+    for (int t = 0; t < T; ++t) total += n_idx[t];
+    if (total >= e->host_pack_min_ids)
+      return upload_ids_hostpacked(e, s, stream, idx, idx_is_i64, n_idx, dst_idx);
   }
   // packed ids of all tables in ONE copy + ONE widening kernel when the caller's streams are
   // equally spaced (one [T, words] buffer), every table has the same count and width, and the
@@ -1547,6 +1660,7 @@ int drs_destroy(drs_engine* e) try {
   cudaSetDevice(e->device);
   for (int i = 0; i < e->n_lanes; ++i)
     if (e->lanes[i].stream) cudaStreamSynchronize(e->lanes[i].stream);
+  if (e->packer) { hostpack_destroy(e->packer); e->packer = nullptr; }
   for (int q = 0; q < e->world; ++q)
     if (q != e->rank && e->peer_slab[q]) cudaIpcCloseMemHandle(e->peer_slab[q]);
   for (float* t : e->tables) cudaFree(t);
@@ -1802,6 +1916,7 @@ static int enqueue_host_on(drs_engine* e, Lane& ln, const float* dense, const vo
   CU(cudaSetDevice(e->device));
   TRY(check_ready(e));
   std::vector<int64_t> n_idx;
+  if (e->packer && !pack_bits) TRY(ensure_pack_staging(e, ln.slot));
   CU(cudaEventRecord(ln.ev[0], ln.stream));
   TRY(upload_inputs(e, ln.slot, ln.stream, dense, idx, idx_is_i64, lengths, batch_size, &n_idx,
                     pack_bits));
@@ -1844,6 +1959,22 @@ int drs_pack_ids(const int32_t* ids, int64_t n_ids, int bits, uint32_t* out) try
     if (fill >= 32) { out[w++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
   }
   while (w < words) { out[w++] = (uint32_t)acc; acc >>= 32; }      // tail + the pad word
+  return DRS_OK;
+} DRS_CATCH
+
+int64_t drs_hostpack_words(int64_t n_ids, int bits) { return pack_block_words(n_ids, bits); }
+
+int drs_hostpack_ids(const void* ids, int idx_is_i64, int64_t n_ids, int bits, int threads,
+                     uint32_t* out, int* ok) try {
+  CHECK_ARG(ids && out && ok && n_ids >= 0, "bad arguments");
+  CHECK_ARG(bits >= 1 && bits <= 31, "bits must be in [1,31]");
+  CHECK_ARG(threads >= 1 && threads <= 256, "threads must be in [1,256]");
+  HostPacker* p = hostpack_create(threads);
+  PackJob jb;
+  jb.ids = ids; jb.is_i64 = idx_is_i64; jb.n = n_ids; jb.bits = bits; jb.out = out;
+  hostpack_run(p, &jb, 1, nullptr, nullptr);
+  hostpack_destroy(p);
+  *ok = jb.ok;
   return DRS_OK;
 } DRS_CATCH
 
@@ -2274,6 +2405,17 @@ int drs_set_option(drs_engine* e, const char* key, int64_t value) try {
   else if (k == "din_fused") e->din_fused = value != 0;
   else if (k == "rnn_tc") e->rnn_tc = value != 0;
   else if (k == "short_fixed") e->short_fixed = value != 0;
+  else if (k == "host_pack") {
+    // value = host threads that pack the ids of a host-path query (0: off)
+    CHECK_ARG(value >= 0 && value <= 256, "host_pack: 0..256 threads");
+    for (int i = 0; i < e->n_lanes; ++i) CU(cudaStreamSynchronize(e->lanes[i].stream));
+    if (e->packer && hostpack_threads(e->packer) != (int)value) {
+      hostpack_destroy(e->packer);
+      e->packer = nullptr;
+    }
+    if (value > 0 && !e->packer) e->packer = hostpack_create((int)value);
+  }
+  else if (k == "host_pack_min_ids") e->host_pack_min_ids = value;
   else if (k == "exchange") {
     CHECK_ARG(value == 0 || value == 1, "exchange must be 0 (fused peer stores) or 1 (unfused)");
     CHECK_ARG(!e->row_mode, "the unfused exchange baseline is table-wise");

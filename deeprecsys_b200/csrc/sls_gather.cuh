@@ -792,4 +792,20 @@ __global__ void k_unpack_ids_multi(const uint32_t* __restrict__ packed, int64_t 
   }
 }
 
+// Lane-interleaved packed blocks written by the host packer (hostpack.h): 512 ids per block,
+// word w of lane l at block[w*16 + l], id r of a block = bits [(r>>4)*bits, +bits) of lane r&15.
+__global__ void k_unpack_ids_blk(const uint32_t* __restrict__ packed, int bits, int64_t n,
+                                 int32_t* __restrict__ dst) {
+  const uint32_t mask = (1u << bits) - 1u;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i & 511), l = r & 15, bit = (r >> 4) * bits;
+    const int w = bit >> 5, sh = bit & 31;
+    const uint32_t* blk = packed + (i >> 9) * (int64_t)(16 * bits);
+    uint32_t v = __ldg(blk + w * 16 + l) >> sh;
+    if (sh + bits > 32) v |= __ldg(blk + (w + 1) * 16 + l) << (32 - sh);
+    dst[i] = (int32_t)(v & mask);
+  }
+}
+
 }  // namespace drs

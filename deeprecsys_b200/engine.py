@@ -388,3 +388,18 @@ def pack_ids(ids, bits, out=None):
         raise ValueError("out must hold %d uint32 words" % words)
     _lib.check(lib.drs_pack_ids(_ptr(ids), ids.shape[0], int(bits), _ptr(out)))
     return out[:words]
+
+
+def hostpack_ids(ids, bits, threads=1):
+    """The engine's own host packer (``drs_hostpack_ids``; lane-interleaved 512-id blocks,
+    csrc/hostpack.h) on int32 or int64 ids -> (uint32 words, ok).  For tests and timing: the
+    serving path packs inside ``drs_enqueue_host`` once ``set_option("host_pack", n)`` is on."""
+    lib = _lib.load()
+    ids = np.ascontiguousarray(ids)
+    if ids.dtype not in (np.int32, np.int64):
+        ids = ids.astype(np.int64)
+    out = np.empty(int(lib.drs_hostpack_words(ids.shape[0], int(bits))), dtype=np.uint32)
+    ok = C.c_int(1)
+    _lib.check(lib.drs_hostpack_ids(_ptr(ids), int(ids.dtype == np.int64), ids.shape[0], int(bits),
+                                    int(threads), _ptr(out), C.byref(ok)))
+    return out, bool(ok.value)

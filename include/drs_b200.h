@@ -183,6 +183,20 @@ int drs_enqueue_host_packed(drs_engine* e, const float* dense, const uint32_t* c
                             const int32_t* bits, const int32_t* const* lengths, int batch_size,
                             float* out_pinned);
 
+/* Engine-side packing: drs_set_option(e, "host_pack", n_threads) makes every host-path call
+ * (drs_infer / drs_enqueue_host / drs_submit_host, int32 or int64 ids — the dtype the reference
+ * hands run_queues, dlrm_s_caffe2.py:223-226,308) pack the ids of tables with <= 2^24 rows on
+ * n host threads into pinned staging, table by table, each table's copy leaving while the next is
+ * packed; queries with fewer than "host_pack_min_ids" lookups (default 65,536) go up unpacked.
+ * Results and the DRS_ERR_INDEX behaviour are those of the unpacked path (a table holding an id
+ * that is negative or past 2^bits is uploaded as it came, and the gather raises the enforce).
+ * The wire layout is engine-internal (lane-interleaved 512-id blocks, csrc/hostpack.h);
+ * drs_hostpack_ids exposes the packer for tests and timing: it packs n int32/int64 ids into
+ * drs_hostpack_words(n, bits) words on `threads` threads; *ok = 0 when some id does not fit. */
+int64_t drs_hostpack_words(int64_t n_ids, int bits);
+int drs_hostpack_ids(const void* ids, int idx_is_i64, int64_t n_ids, int bits, int threads,
+                     uint32_t* out, int* ok);
+
 /* Submit / wait pair for pipelined serving: up to drs_lane_count() queries may be in flight
  * (the copy and MLP kernels of one overlap the gather of the next).  out_pinned (nullable) must
  * be pinned host memory and stay valid until drs_wait(ticket) returns; drs_wait reports the

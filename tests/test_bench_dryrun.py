@@ -57,7 +57,17 @@ def test_single_gpu_line_carries_every_secondary_config():
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0
     assert d["roofline"]["bound"] == "hbm" and d["roofline"]["unit"] == "GB/s"
     assert d["roofline"]["alg_bytes_per_sample"] == 84512
-    assert d["e2e"]["h2d_bytes_per_step"] == 64 * (8 * 80 * 4 + 8 * 4 + 128 * 4)
+    e2e = d["e2e"]
+    assert e2e["plain"]["h2d_bytes_per_step"] == 64 * (8 * 80 * 4 + 8 * 4 + 128 * 4)
+    assert e2e["mode"] in ("plain", "host_pack") and e2e["host_pack"][0]["host_threads"] >= 1
+    # lane-interleaved 512-id blocks: 10 blocks x 16 lanes x `bits` words per table (the dry
+    # run's tables are cut down, so fewer bits than the shipped 22)
+    packed_id_bytes = e2e["host_pack"][0]["h2d_bytes_per_step"] - 64 * (8 * 4 + 128 * 4)
+    assert packed_id_bytes % (8 * 10 * 16 * 4) == 0 and 1 <= packed_id_bytes // 5120 <= 22
+    assert e2e["h2d_bytes_per_step"] == (e2e["plain"] if e2e["mode"] == "plain"
+                                         else e2e["host_pack"][0])["h2d_bytes_per_step"] \
+        or len(e2e["host_pack"]) > 1
+    assert e2e["int64_ids"]["plain"]["value"] > 0 and e2e["int64_ids"]["host_pack"]["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["parity"]["ok"] and d["parity"]["pooled"] == "bit-exact"
     assert d["sharded"] is None
