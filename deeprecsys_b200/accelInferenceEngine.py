@@ -76,6 +76,8 @@ class AccelBackend(object):
         # so capturing CUDA graphs of single steps would only cost; load is absorbed by coalescing
         self.engine.set_option("cuda_graphs", 0)
         self.engine.create()                               # tables -> MLPs, reference draw order
+        if int(getattr(args, "accel_host_pack", 0) or 0) > 0:
+            self.engine.set_option("host_pack", int(args.accel_host_pack))
         self.spec = self.engine.spec
         self.upload = bool(getattr(args, "accel_upload_inputs", False))
         T = self.spec.T

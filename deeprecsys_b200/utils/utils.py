@@ -128,6 +128,9 @@ ACCEL_FLAGS = (
     ("accel_lanes", int, 0),             # queries in flight on the GPU (0 = library default, 2)
     ("accel_responder", int, 1),         # 1: ServiceResponses are built and sent by a helper
                                          # process fed through a shared-memory ring
+    ("accel_host_pack", int, 0),         # host threads that bit-pack the ids of queries carrying
+                                         # their own inputs before the copy (0 = ids travel as
+                                         # they are; pays for queries of >= 65,536 lookups)
     ("data_trace_sort_lookups", _T, False),  # --data_generation synthetic: sort the ids inside
                                          # every lookup (the random generator's np.unique does)
 )
