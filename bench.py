@@ -98,10 +98,10 @@ def parse_args():
     p.add_argument("--no_system", action="store_true",
                    help="skip the Poisson-arrival serving run through the Queue API")
     p.add_argument("--system_rates_ms", type=str,
-                   default="0.25,0.06,0.03,0.02,0.014,0.011,0.009,0.0075,0.0065",
+                   default="0.25,0.06,0.03,0.02,0.014,0.009,0.007,0.0055,0.0045,0.0038",
                    help="mean inter-arrival times (ms) of the serving run")
     p.add_argument("--system_queries", type=int, default=6000)
-    p.add_argument("--system_generators", type=int, default=3,
+    p.add_argument("--system_generators", type=int, default=4,
                    help="load-generator processes of the serving run (Poisson streams of "
                         "rate / G each)")
     p.add_argument("--seed", type=int, default=123)

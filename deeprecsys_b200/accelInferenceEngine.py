@@ -38,10 +38,10 @@ import traceback
 import numpy as np
 
 try:                                   # running inside a DeepRecSys checkout
-    from utils.packets import ServiceResponse
+    from utils.packets import ServiceRequest, ServiceResponse
     from utils.utils import debugPrint
 except ImportError:                    # standalone
-    from deeprecsys_b200.utils.packets import ServiceResponse
+    from deeprecsys_b200.utils.packets import ServiceRequest, ServiceResponse
     from deeprecsys_b200.utils.utils import debugPrint
 
 # the reference's whitelist (accelInferenceEngine.py:37) plus ncf
@@ -168,7 +168,7 @@ class AccelBackend(object):
         start at sum(batch_sizes[:k]) of the completed buffer."""
         buf, out_ptr = self._next_out()
         ticket = self.engine.submit_many(batch_ids, batch_sizes, out_ptr)
-        return ("ticket", ticket, buf, int(sum(batch_sizes)))
+        return ("ticket", ticket, buf, int(np.sum(batch_sizes)))
 
     @property
     def can_coalesce(self):
@@ -449,6 +449,169 @@ def _spawn_responder(args, responseQueue, engine_id, multi):
         return None, None
 
 
+def _wire_codec(args, backend, engine_id, reader, writer, multi, coalesce, pipelined):
+    """The C wire codec for this engine, or None when the record path does not apply: several
+    consumers on the queue, non-stock queues, one launch per request, debug prints, score dumps,
+    DRS_ACCEL_WIRE=0, or a codec that fails its self-check against ``pickle``."""
+    if (multi or reader is None or not reader.fast or not writer.fast or coalesce <= 1
+            or not pipelined or backend is None or getattr(backend, "dump_dir", None)
+            or getattr(args, "debug_mode", False) or os.environ.get("DRS_ACCEL_WIRE") == "0"
+            or not hasattr(backend, "nbatches")):
+        return None
+    try:
+        from deeprecsys_b200.utils.wire import WireCodec
+        codec = WireCodec(ServiceResponse, engine_id)
+        if not codec.self_check(ServiceRequest):
+            print("[Accel] wire codec failed its self-check against pickle; packets stay Python "
+                  "objects")
+            return None
+        return codec
+    except Exception as exc:
+        print("[Accel] wire codec unavailable (%r); packets stay Python objects" % (exc,))
+        return None
+
+
+def _serve_records(args, backend, codec, reader, requestQueue, responseQueue, depth, coalesce,
+                   stack_rows):
+    """Serving loop over packet RECORDS (utils/wire.py): request frames are parsed in C straight
+    from the pipe's bytes into a numpy record array, groups of waiting requests are cut with
+    array arithmetic and served by ONE stacked launch each (``drs_submit_many``), and the
+    ServiceResponse frames of a finished group are emitted in C and written with one ``write``.
+    Same protocol, same fields, same order of events as the object loop below
+    (accelInferenceEngine.py:46-83 of the reference: pull, serve, respond) — without a Python
+    object per packet.
+
+    Returns when the next frame on the pipe is not a plain ServiceRequest (the final ``None``, a
+    request that carries tensors, an odd field type): everything before it has been answered,
+    the frame and what follows are left in ``reader._buf`` for the object loop."""
+    import collections
+    from deeprecsys_b200.utils.wire import PYTHON
+    fd, poll, rlock = reader._fd, reader._poll, requestQueue._rlock
+    release = requestQueue._sem.release
+    wfd, wlock, acquire = responseQueue._writer.fileno(), responseQueue._wlock, \
+        responseQueue._sem.acquire
+    nbatches = int(backend.nbatches)
+    max_rows = int(args.max_mini_batch_size)
+    coalesce = min(int(coalesce), 32)                      # drs_submit_many: <= 32 requests
+    # int fields of batch_id (index 1) and batch_size (index 2) must be plain ints
+    kind_mask = (3 << 2) | (3 << 4)
+    buf = reader._buf
+    inflight = collections.deque()                         # (records, handle, rows)
+    st = {"recs": None, "head": 0, "bail": False}
+
+    def pull(block):
+        nonlocal buf
+        while True:
+            if len(buf) >= 4:
+                recs, consumed, stop = codec.parse(buf)
+                if consumed:
+                    buf = buf[consumed:]
+                n = len(recs)
+                if stop == PYTHON:
+                    st["bail"] = True
+                if n:
+                    for _ in range(n):
+                        release()                          # Queue.get: a free slot per packet
+                    recs["start_time"] = time.time()
+                    sizes = recs["batch_size"]
+                    ok = ((sizes >= 1) & (sizes <= max_rows) & (recs["batch_id"] >= 0)
+                          & (recs["batch_id"] < nbatches) & ((recs["kinds"] & kind_mask) == 0))
+                    st["recs"], st["head"] = recs, 0
+                    st["ok"] = ok
+                    st["bad"] = np.flatnonzero(~ok)
+                    st["cum"] = np.cumsum(np.where(ok, sizes, 0))
+                    st["ids32"] = recs["batch_id"].astype(np.int32)
+                    st["sizes32"] = np.where(ok, sizes, 0).astype(np.int32)
+                    return True
+                if st["bail"]:
+                    return False
+            if not block and not poll.poll(0):
+                return False
+            with rlock:
+                chunk = os.read(fd, 1 << 16)
+            if not chunk:
+                raise EOFError("queue pipe closed")
+            buf = buf + chunk if buf else chunk
+            block = False                                  # parse what came; wait again if partial
+            if len(buf) < 4:
+                block = True
+
+    def respond(recs):
+        blob = codec.emit(recs)
+        for _ in range(len(recs)):
+            acquire()                                      # Queue.put: a slot per packet
+        with wlock:
+            while blob:
+                blob = blob[os.write(wfd, blob):]
+
+    def finish_oldest():
+        recs, handle, rows = inflight.popleft()
+        try:
+            out = backend.complete(handle)
+            if int(out.shape[0]) != rows:
+                raise RuntimeError("coalesced launch returned %d rows for %d" % (out.shape[0], rows))
+            recs["out_batch_size"] = recs["batch_size"]
+        except Exception as exc:                           # keep serving: the parent counts responses
+            print("[Accel] request failed: %r" % (exc,))
+            sys.stdout.flush()
+            recs["out_batch_size"] = 0
+        recs["end_time"] = time.time()
+        respond(recs)
+
+    while True:
+        if len(inflight) >= depth:
+            finish_oldest()
+            continue
+        recs, head = st["recs"], st["head"]
+        if recs is None or head >= len(recs):
+            if st["bail"]:
+                break
+            st["recs"] = None
+            if not pull(block=not inflight):
+                if inflight:
+                    finish_oldest()                        # nothing waiting: complete the oldest
+                continue
+            recs, head = st["recs"], 0
+        if not st["ok"][head]:
+            bad = recs[head:head + 1]                      # refused: answered with 0 rows at once
+            print("[Accel] request refused: batch_id %d, batch_size %d"
+                  % (int(bad["batch_id"][0]), int(bad["batch_size"][0])))
+            sys.stdout.flush()
+            bad["out_batch_size"] = 0
+            bad["end_time"] = time.time()
+            respond(bad)
+            st["head"] = head + 1
+            continue
+        # every valid request that is already here: up to `coalesce` requests / stack_rows samples
+        cum, end = st["cum"], min(len(recs), head + coalesce)
+        nb = st["bad"]
+        if len(nb):
+            k = int(np.searchsorted(nb, head))
+            if k < len(nb):
+                end = min(end, int(nb[k]))
+        base = int(cum[head - 1]) if head else 0
+        end = min(end, int(np.searchsorted(cum, base + stack_rows, side="right")))
+        end = max(end, head + 1)
+        group = recs[head:end]
+        rows = int(cum[end - 1]) - base
+        try:
+            if end - head == 1:                            # a lone request: the ordinary launch
+                handle = backend.submit(int(st["ids32"][head]), rows)
+            else:
+                handle = backend.submit_many(st["ids32"][head:end], st["sizes32"][head:end])
+            inflight.append((group, handle, rows))
+        except Exception as exc:
+            print("[Accel] coalesced launch refused: %r" % (exc,))
+            sys.stdout.flush()
+            group["out_batch_size"] = 0
+            group["end_time"] = time.time()
+            respond(group)
+        st["head"] = end
+    while inflight:
+        finish_oldest()
+    reader._buf = buf
+
+
 def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):
     np.random.seed(args.numpy_rand_seed)
     np.set_printoptions(precision=args.print_precision)
@@ -513,6 +676,14 @@ def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibli
             and getattr(backend, "can_coalesce", True)):
         coalesce = max(1, int(getattr(args, "accel_coalesce", 1) or 1))
     stack_rows = int(getattr(backend, "stack_rows", 0) or getattr(args, "max_mini_batch_size", 0))
+
+    # Packets as records: frames are parsed / emitted in C and the loop works on numpy record
+    # arrays (utils/wire.py) until a frame needs the Python path — the final None at the latest —
+    # which the object loop below then handles (everything before it has been answered).
+    codec = _wire_codec(args, backend, engine_id, reader, writer, multi, coalesce, pipelined)
+    if codec is not None:
+        _serve_records(args, backend, codec, reader, requestQueue, responseQueue, depth, coalesce,
+                       stack_rows)
 
     def respond_many(entries, out_sizes):
         """One response per request; out_sizes[i] = rows answered for entries[i] (0 = failed)."""

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 # host-only translation units (g++: GCC vector extensions + per-ISA clones, which nvcc's front
 # end does not take); linked into the same .so
-HOST_SOURCES = ["hostpack.cpp"]
+HOST_SOURCES = ["hostpack.cpp", "wire.cpp"]
 HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-pthread"]
 
 NVCC_FLAGS = [
@@ -63,8 +63,8 @@ def build(force=False, verbose=False):
     objs = []
     for src in HOST_SOURCES:
         obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
-        hcmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + ["-c", os.path.join(CSRC, src),
-                                                              "-o", obj]
+        hcmd = [os.environ.get("CXX", "g++")] + HOST_FLAGS + ["-I", INCLUDE, "-c",
+                                                              os.path.join(CSRC, src), "-o", obj]
         hp = subprocess.run(hcmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if verbose or hp.returncode != 0:
             sys.stderr.write(hp.stdout)

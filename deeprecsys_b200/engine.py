@@ -224,8 +224,14 @@ class AccelEngine(object):
         pass of the MLPs, one D2H copy.  Row r of request k lands at row
         ``sum(batch_sizes[:k]) + r`` of the output.  Returns a ticket for ``wait``."""
         n = len(batch_ids)
-        ids = (C.c_int32 * n)(*batch_ids)
-        sizes = (C.c_int32 * n)(*batch_sizes)
+        if isinstance(batch_ids, np.ndarray) and isinstance(batch_sizes, np.ndarray):
+            # the record loop hands int32 arrays: no per-request Python work
+            keep = (np.ascontiguousarray(batch_ids, dtype=np.int32),
+                    np.ascontiguousarray(batch_sizes, dtype=np.int32))
+            ids, sizes = (a.ctypes.data_as(C.POINTER(C.c_int32)) for a in keep)
+        else:
+            ids = (C.c_int32 * n)(*batch_ids)
+            sizes = (C.c_int32 * n)(*batch_sizes)
         t = C.c_int64()
         _lib.check(self.lib.drs_submit_many(self._handle, n, ids, sizes, out_ptr, C.byref(t)))
         return t.value

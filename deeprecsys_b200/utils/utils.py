@@ -122,10 +122,14 @@ ACCEL_FLAGS = (
     ("accel_upload_inputs", _T, False),  # H2D per query instead of pre-staged batches
     ("accel_gpus", int, 1),              # GPUs behind the single accel slot (replicas; sibling
                                          # processes share accelRequestQueue / responseQueue)
-    ("accel_coalesce", int, 16),         # requests already waiting on the accel queue that one
-                                         # launch may serve together (1 = one launch per request)
-    ("accel_stack_rows", int, 4096),     # most samples one coalesced launch stacks
-    ("accel_lanes", int, 0),             # queries in flight on the GPU (0 = library default, 2)
+    ("accel_coalesce", int, 32),         # requests already waiting on the accel queue that one
+                                         # launch may serve together (1 = one launch per request;
+                                         # drs_submit_many takes at most 32)
+    ("accel_stack_rows", int, 16384),    # most samples one coalesced launch stacks
+    ("accel_lanes", int, 3),             # launches in flight on the GPU (0 = library default, 2).
+                                         # B200, RMC1, queries ~ normal(256, 32): 16 / 4096 / 2
+                                         # saturate at 134 k queries/s, 32 / 16384 / 3 at 219 k
+                                         # (profiles/r02r_*, r02s_*)
     ("accel_responder", int, 1),         # 1: ServiceResponses are built and sent by a helper
                                          # process fed through a shared-memory ring
     ("accel_host_pack", int, 0),         # host threads that bit-pack the ids of queries carrying

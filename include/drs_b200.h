@@ -309,6 +309,38 @@ int drs_exchange_begin(drs_engine* e, int batch_id, int batch_size, void** send,
                        int64_t* floats_per_peer, void** stream);
 int drs_exchange_end(drs_engine* e);
 
+/* Queue wire codec of the serving loop (host only; csrc/wire.cpp).  The reference's serving
+ * protocol is pickled packets over multiprocessing Queues: a frame on the pipe is
+ * struct.pack("!i", len) + pickle.dumps(obj) (DeepRecSys.py:44-66, loadGenerator.py:162-177,
+ * accelInferenceEngine.py:46-83, utils/packets.py:6-59).  One record per packet, the layout of
+ * deeprecsys_b200/utils/response_ring.py REC: `kinds` holds two bits per field (epoch, batch_id,
+ * batch_size, sub_id, total_sub_batches, exp_packet, arrival_time): 0 int / float, 1 bool,
+ * 2 None.
+ *   drs_wire_parse_requests: decodes the leading frames of buf[0, len) that are exactly a pickled
+ *     `ServiceRequest` with int / bool / None fields (arrival_time: float / None) into recs;
+ *     *consumed = bytes of the decoded frames; *stop says why it stopped: NEED_MORE (the rest is
+ *     an incomplete frame), FULL (max_recs reached), PYTHON (the next frame is something else —
+ *     the final None, a request carrying tensors, an unexpected type: the caller unpickles it).
+ *   drs_wire_emit_responses: recs -> frames holding pickled `ServiceResponse` objects
+ *     (protocol 4).  class_ops = the pickle opcodes that push the class (SHORT_BINUNICODE module,
+ *     MEMOIZE, SHORT_BINUNICODE qualname, MEMOIZE, STACK_GLOBAL, MEMOIZE); field_order[12] = the
+ *     attribute order of the class' __dict__ as indices into (consumer_id, epoch, batch_id,
+ *     batch_size, arrival_time, queue_start_time, queue_end_time, inference_end_time,
+ *     out_batch_size, total_sub_batches, exp_packet, sub_id); queue_end_time and
+ *     inference_end_time are both rec.end_time, queue_start_time is rec.start_time
+ *     (accelInferenceEngine.py:68-80). */
+typedef struct drs_wire_rec {
+  int64_t epoch, batch_id, batch_size, sub_id, total_sub_batches, out_batch_size, exp_packet,
+      kinds;
+  double arrival_time, start_time, end_time;
+} drs_wire_rec;
+enum { DRS_WIRE_NEED_MORE = 0, DRS_WIRE_PYTHON = 1, DRS_WIRE_FULL = 2 };
+int drs_wire_parse_requests(const uint8_t* buf, int64_t len, drs_wire_rec* recs, int max_recs,
+                            int32_t* n_recs, int64_t* consumed, int32_t* stop);
+int drs_wire_emit_responses(const drs_wire_rec* recs, int n, const uint8_t* class_ops,
+                            int class_ops_len, const int32_t* field_order, int64_t consumer_id,
+                            uint8_t* out, int64_t cap, int64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

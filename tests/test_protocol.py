@@ -215,6 +215,7 @@ class CoalescingBackend(PipelinedBackend):
     depth = 2
     stack_rows = 150
     can_coalesce = True
+    nbatches = 6                                   # staged batches: lets the record loop run
 
     def submit_many(self, batch_ids, sizes):
         with open(os.path.join(os.environ["DRS_TEST_PID_DIR"], "groups"), "a") as f:
@@ -230,13 +231,17 @@ class CoalescingBackend(PipelinedBackend):
         return np.full((sum(handle[2]), 1), 0.5, np.float32)
 
 
-@pytest.mark.parametrize("responder", [1, 0])
-def test_coalesced_serving_answers_every_request_exactly_once(tmp_path, monkeypatch, responder):
+@pytest.mark.parametrize("responder,wire", [(1, "1"), (1, "0"), (0, "0")],
+                         ids=["records", "objects+responder", "objects"])
+def test_coalesced_serving_answers_every_request_exactly_once(tmp_path, monkeypatch, responder,
+                                                              wire):
     """--accel_coalesce: requests that are already waiting are served by one launch; every request
-    still gets its own ServiceResponse with its own fields (through the responder helper process
-    or in-process), a failed launch answers all of its requests with 0, the final sentinel comes
-    after the last response."""
+    still gets its own ServiceResponse with its own fields (packets as records parsed / emitted
+    in C, or as Python objects answered through the responder helper process or in-process), a
+    failed launch answers all of its requests with 0, the final sentinel comes after the last
+    response."""
     monkeypatch.setenv("DRS_TEST_PID_DIR", str(tmp_path))
+    monkeypatch.setenv("DRS_ACCEL_WIRE", wire)
     reqs = [_req(3 if i in (40, 41, 150) else i % 3, 10 + i % 50, epoch=i) for i in range(240)]
     reqs[17].exp_packet = True
     reqs[18].sub_id, reqs[18].total_sub_batches = 2, 5
@@ -259,6 +264,38 @@ def test_coalesced_serving_answers_every_request_exactly_once(tmp_path, monkeypa
     assert any(r.batch_id == 3 for r in zero)
     assert any(r.batch_id == 3 and r.out_batch_size == 0 for r in out)
     assert len(zero) <= 3 * 8
+
+
+def test_record_loop_hands_over_to_the_object_loop_and_back_to_nothing(tmp_path, monkeypatch):
+    """Packets travel as records until a frame needs Python (here: a str field, then a request
+    with an extra attribute); from there the object loop serves — nothing is lost, duplicated or
+    reordered across the hand-over, odd values come back untouched, bad requests get 0 rows."""
+    monkeypatch.setenv("DRS_TEST_PID_DIR", str(tmp_path))
+    monkeypatch.setenv("DRS_ACCEL_WIRE", "1")
+    reqs = [_req(i % 3, 10 + i % 40, epoch=i) for i in range(120)]
+    reqs[5].batch_size = 0                                 # refused in the record loop
+    reqs[6].batch_id = 99                                  # no such staged batch
+    reqs[7].batch_size = None
+    reqs[30].sub_id, reqs[30].total_sub_batches = None, True
+    reqs[60].exp_packet = "yes"                            # -> pickle.loads, object loop from here
+    reqs[90].colour = "blue"
+    out = _run_engine(CoalescingBackend, reqs, extra=["--accel_coalesce", "8"])
+    assert len(out) == len(reqs)
+    by_epoch = {r.epoch: r for r in out}
+    assert sorted(by_epoch) == list(range(120))
+    for q in reqs:
+        r = by_epoch[q.epoch]
+        for name in ("batch_id", "batch_size", "sub_id", "total_sub_batches", "exp_packet",
+                     "arrival_time"):
+            a, b = getattr(r, name), getattr(q, name)
+            assert a == b and type(a) is type(b), (q.epoch, name, a, b)
+        assert r.consumer_id == 7 and r.queue_start_time <= r.queue_end_time == r.inference_end_time
+    assert [by_epoch[e].out_batch_size for e in (5, 6, 7)] == [0, 0, 0]
+    assert all(by_epoch[e].out_batch_size == reqs[e].batch_size
+               for e in range(120) if e not in (5, 6, 7))
+    # the first sixty were answered before anything after the hand-over
+    order = [r.epoch for r in out]
+    assert max(order.index(e) for e in range(60)) < min(order.index(e) for e in range(60, 120))
 
 
 def test_engine_without_queue_exits_like_the_reference():

@@ -47,6 +47,21 @@ def test_responder_process_rebuilds_the_reference_responses(n):
     reqs[0].exp_packet = True
     if n > 2:
         reqs[2].sub_id, reqs[2].total_sub_batches, reqs[2].arrival_time = None, None, None
+    # the parent reads while it produces (as DeepRecSys.py's loop does): 300 responses are more
+    # than the response pipe + the ring hold, a producer that only reads afterwards would wait
+    # on a full ring for a responder that waits on a full pipe
+    import threading
+    got = []
+
+    def collect():
+        while True:
+            item = resp_q.get(timeout=60)
+            if item is None:
+                break
+            got.append(item)
+
+    reader = threading.Thread(target=collect)
+    reader.start()
     for i in range(0, n, 7):
         rows = []
         for r in reqs[i:i + 7]:
@@ -54,12 +69,8 @@ def test_responder_process_rebuilds_the_reference_responses(n):
             rows.append(vals[:5] + (int(r.batch_size) - 1, vals[5], kinds, at, 5.0, 6.0))
         ring.push(rows)
     ring.push([(0, 0, 0, 0, 0, 0, 0, R.KIND_SENTINEL, 0.0, 0.0, 0.0)])
-    got = []
-    while True:
-        item = resp_q.get(timeout=30)
-        if item is None:
-            break
-        got.append(item)
+    reader.join(timeout=90)
+    assert not reader.is_alive()
     proc.join(timeout=30)
     assert not proc.is_alive() and len(got) == n
     for r, q in zip(got, reqs):
