@@ -101,9 +101,9 @@ def parse_args():
                    default="0.25,0.06,0.03,0.02,0.014,0.009,0.007,0.0055,0.0045,0.0038",
                    help="mean inter-arrival times (ms) of the serving run")
     p.add_argument("--system_queries", type=int, default=6000)
-    p.add_argument("--system_generators", type=int, default=4,
+    p.add_argument("--system_generators", type=int, default=0,
                    help="load-generator processes of the serving run (Poisson streams of "
-                        "rate / G each)")
+                        "rate / G each); 0 = 4 when the box has >= 8 cores per GPU, else 3")
     p.add_argument("--seed", type=int, default=123)
     p.add_argument("--locality", type=str, default=None,
                    help="ids with temporal reuse instead of uniform-random ones: a stack-distance "
@@ -975,13 +975,15 @@ def run_system(env, opts):
     # a fresh interpreter: the harness forks the engine process (as DeepRecSys.py does), and a
     # forked child cannot use CUDA once its parent — this process — has initialised it
     cfg = os.path.join(CONFIG_DIR, CONFIGS[opts.config])
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8
+    generators = opts.system_generators or (4 if cores // max(1, env.world) >= 8 else 3)
     cmd = [sys.executable, "-m", "deeprecsys_b200.serve", "--config_file", cfg,
            "--num_batches", "32", "--max_mini_batch_size", "1024",
            "--batch_size_distribution", "normal", "--avg_mini_batch_size", "256",
            "--var_mini_batch_size", "32", "--model_accel", "--queue",
            "--numpy_rand_seed", str(opts.seed + env.rank), "--accel_precision", opts.precision,
            "--accel_device", str(env.local), "--serve_queries", str(opts.system_queries),
-           "--serve_generators", str(opts.system_generators)]
+           "--serve_generators", str(generators)]
     if opts.system_rates_ms:
         cmd += ["--serve_rates_ms", opts.system_rates_ms]
     try:
