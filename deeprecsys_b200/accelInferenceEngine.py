@@ -373,6 +373,12 @@ def accelInferenceEngine(args,
               "deeprecsys_b200.serve directly")
         sys.stdout.flush()
         sys.exit()
+    # under the reference's own cli() (a DeepRecSys checkout: utils/utils.py is theirs) the
+    # namespace has none of this backend's flags: they take their defaults, as with our cli()
+    from deeprecsys_b200.utils.utils import ACCEL_FLAGS
+    for name, _type, default in ACCEL_FLAGS:
+        if not hasattr(args, name):
+            setattr(args, name, default)
     _engine_process(args, requestQueue, engine_id, responseQueue, inferenceEngineReadyQueue,
                     sibling=False)
 
@@ -451,10 +457,10 @@ def _spawn_responder(args, responseQueue, engine_id, multi):
 
 def _wire_codec(args, backend, engine_id, reader, writer, multi, coalesce, pipelined):
     """The C wire codec for this engine, or None when the record path does not apply: several
-    consumers on the queue, non-stock queues, one launch per request, debug prints, score dumps,
+    consumers on the queue, non-stock queues, one launch per request, debug prints,
     DRS_ACCEL_WIRE=0, or a codec that fails its self-check against ``pickle``."""
     if (multi or reader is None or not reader.fast or not writer.fast or coalesce <= 1
-            or not pipelined or backend is None or getattr(backend, "dump_dir", None)
+            or not pipelined or backend is None
             or getattr(args, "debug_mode", False) or os.environ.get("DRS_ACCEL_WIRE") == "0"
             or not hasattr(backend, "nbatches")):
         return None
@@ -497,7 +503,8 @@ def _serve_records(args, backend, codec, reader, requestQueue, responseQueue, de
     kind_mask = (3 << 2) | (3 << 4)
     buf = reader._buf
     inflight = collections.deque()                         # (records, handle, rows)
-    st = {"recs": None, "head": 0, "bail": False}
+    st = {"recs": None, "head": 0, "bail": False, "served": 0}
+    dump_dir = getattr(backend, "dump_dir", None)
 
     def pull(block):
         nonlocal buf
@@ -551,12 +558,20 @@ def _serve_records(args, backend, codec, reader, requestQueue, responseQueue, de
             if int(out.shape[0]) != rows:
                 raise RuntimeError("coalesced launch returned %d rows for %d" % (out.shape[0], rows))
             recs["out_batch_size"] = recs["batch_size"]
+            if dump_dir:                                   # the parity side channel (packets
+                row = 0                                    # carry no tensors)
+                for r in recs:
+                    n = int(r["batch_size"])
+                    np.save(os.path.join(dump_dir, "accel_e%s_b%s_n%s.npy" % (
+                        int(r["epoch"]), int(r["batch_id"]), n)), np.array(out[row:row + n]))
+                    row += n
         except Exception as exc:                           # keep serving: the parent counts responses
             print("[Accel] request failed: %r" % (exc,))
             sys.stdout.flush()
             recs["out_batch_size"] = 0
         recs["end_time"] = time.time()
         respond(recs)
+        st["served"] += len(recs)
 
     while True:
         if len(inflight) >= depth:
@@ -610,6 +625,9 @@ def _serve_records(args, backend, codec, reader, requestQueue, responseQueue, de
     while inflight:
         finish_oldest()
     reader._buf = buf
+    if os.environ.get("DRS_ACCEL_WIRE_REPORT") == "1":
+        print("[Accel] record loop answered %d packets" % st["served"])
+        sys.stdout.flush()
 
 
 def _engine_loop(args, requestQueue, engine_id, responseQueue, readyQueue, sibling):

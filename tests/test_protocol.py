@@ -364,15 +364,46 @@ _m.BACKEND_FACTORY = OracleBackend        # CPU test tier only: no GPU here
 accelInferenceEngine = _m.accelInferenceEngine
 """
 SHIM_CPU = "from oracle.cpu_inference_engine import inferenceEngine\n"
+# the same oracle behind the submit / submit_many / complete surface of the GPU backend, so that
+# the engine serves the reference's packets as records (C wire codec + coalesced launches)
+SHIM_ACCEL_RECORDS = """
+import numpy as np
+from deeprecsys_b200 import accelInferenceEngine as _m
+from oracle.cpu_inference_engine import OracleBackend
+
+
+class PipelinedOracle(OracleBackend):        # CPU test tier only: no GPU here
+    depth, can_coalesce, stack_rows = 2, True, 256
+
+    def submit(self, batch_id, batch_size):
+        return ("done", self.serve(int(batch_id), int(batch_size)))
+
+    def submit_many(self, batch_ids, sizes):
+        return ("done", np.concatenate([self.serve(int(b), int(n))
+                                        for b, n in zip(batch_ids, sizes)]))
+
+    def complete(self, handle):
+        return handle[1]
+
+
+_m.BACKEND_FACTORY = PipelinedOracle
+accelInferenceEngine = _m.accelInferenceEngine
+"""
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
-@pytest.mark.parametrize("cpu_engine", ["torch_port", "reference_over_caffe2_shim"])
+@pytest.mark.parametrize("cpu_engine", ["torch_port", "reference_over_caffe2_shim",
+                                        "torch_port+records"])
 def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_path, cpu_engine):
     """cpu_engine = reference_over_caffe2_shim: every file of the system except
     accelInferenceEngine.py is the reference's own (DeepRecSys.py, loadGenerator.py,
     scheduler.py, inferenceEngine.py, models/, data_generator/, utils/), with the Caffe2
-    operator runtime supplied by oracle/caffe2_shim."""
+    operator runtime supplied by oracle/caffe2_shim.
+    +records: the accel engine serves the packets the reference's loadGenerator pickles
+    (``utils.packets.ServiceRequest``) as records — frames parsed in C, coalesced launches,
+    ``ServiceResponse`` frames emitted in C — and the reference's own main loop unpickles them."""
+    records = cpu_engine.endswith("+records")
+    cpu_engine = cpu_engine.split("+")[0]
     stage = tmp_path / "drs"
     stage.mkdir()
     names = ["DeepRecSys.py", "loadGenerator.py", "scheduler.py", "utils"]
@@ -384,11 +415,12 @@ def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_pat
         (stage / "inferenceEngine.py").write_text(SHIM_CPU)
     for name in names:
         os.symlink(os.path.join(REF, name), stage / name)
-    (stage / "accelInferenceEngine.py").write_text(textwrap.dedent(SHIM_ACCEL))
+    (stage / "accelInferenceEngine.py").write_text(
+        textwrap.dedent(SHIM_ACCEL_RECORDS if records else SHIM_ACCEL))
     dump = tmp_path / "dump"
     dump.mkdir()
     env = dict(os.environ, PYTHONPATH=pypath, DRS_ACCEL_DUMP_DIR=str(dump),
-               PYTHONWARNINGS="ignore")
+               PYTHONWARNINGS="ignore", DRS_ACCEL_WIRE_REPORT="1")
     argv = SMALL_SYSTEM + ["--queue", "--model_accel", "--inference_engines", "1",
                            "--nepochs", "2", "--batch_size_distribution", "normal",
                            "--avg_mini_batch_size", "32", "--var_mini_batch_size", "16",
@@ -407,6 +439,9 @@ def test_unmodified_reference_orchestrator_runs_against_our_accel_engine(tmp_pat
     line = [l for l in out.splitlines() if l.startswith("Accel requests")][0]
     n_accel = int(line.split()[2])
     assert n_accel > 0
+    served_as_records = [int(l.split()[-2]) for l in out.splitlines()
+                         if l.startswith("[Accel] record loop answered")]
+    assert (served_as_records and served_as_records[0] > 0) if records else not served_as_records
     dumps = sorted(glob.glob(str(dump / "*.npy")))
     assert len(dumps) > 0
     # the accel process regenerated the same data/parameters as an independent CPU restatement
