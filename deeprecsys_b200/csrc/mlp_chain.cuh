@@ -24,8 +24,14 @@ namespace drs {
 
 constexpr int kChainMaxLayers = 4;
 constexpr int kChainBK = 16;                 // fp32 per chunk = one 64-byte swizzle row
-constexpr int kChainASlots = 4;              // A ring: [128 x 16] hi + lo = 16 KB per slot
-constexpr int kChainBSlots = 3;              // B ring: [256 x 16] hi + lo = 32 KB per slot (3 slots: the
+#ifndef DRS_CHAIN_A_SLOTS
+#define DRS_CHAIN_A_SLOTS 4
+#endif
+#ifndef DRS_CHAIN_B_SLOTS
+#define DRS_CHAIN_B_SLOTS 3
+#endif
+constexpr int kChainASlots = DRS_CHAIN_A_SLOTS;   // A ring: [128 x 16] hi + lo = 16 KB per slot
+constexpr int kChainBSlots = DRS_CHAIN_B_SLOTS;   // B ring: [256 x 16] hi + lo = 32 KB per slot (3 slots: the
                                              // CTA must fit beside 2 persistent gather CTAs per SM)
 constexpr int kChainABytes = kTcBM * kChainBK * 4;            // 8 KB (one of hi / lo)
 constexpr int kChainBBytes = 256 * kChainBK * 4;              // 16 KB (one of hi / lo, BN = 256)
