@@ -34,8 +34,14 @@ namespace drs {
 #ifndef DRS_SLS_UNROLL
 #define DRS_SLS_UNROLL 8
 #endif
-#ifndef DRS_SLS_MIN_CTAS
-#define DRS_SLS_MIN_CTAS 1                 // persistent gather: min resident CTAs the register budget allows
+// DRS_SLS_MIN_CTAS (tuning builds only): register cap of the persistent gather as "min resident
+// CTAs per SM" (5 -> 48 registers).  Undefined in the product: a second __launch_bounds__
+// argument — even 1 — changes ptxas' allocation (96 registers instead of 64, i.e. 2 CTAs per SM
+// instead of 4; measured as 360 M instead of 515 M inf/s on 8 GPUs, profiles/r02v_*).
+#ifdef DRS_SLS_MIN_CTAS
+#define DRS_SLS_PERSIST_BOUNDS __launch_bounds__(kSlsThreads, DRS_SLS_MIN_CTAS)
+#else
+#define DRS_SLS_PERSIST_BOUNDS __launch_bounds__(kSlsThreads)
 #endif
 constexpr int kSlsThreads = DRS_SLS_THREADS;
 constexpr int kSlsUnroll = DRS_SLS_UNROLL;
@@ -410,7 +416,7 @@ __host__ __device__ inline size_t sls_persist_smem_bytes(int T, int SB, int idx_
 // occupancy of the HBM-bound long-segment kernel.
 // MULTI: the tiles enumerate the requests of SlsLaunch::pk instead of one query.
 template <int LPR, bool SHORT, bool MULTI = false>
-__global__ void __launch_bounds__(kSlsThreads, DRS_SLS_MIN_CTAS) k_sls_gather_persist(const SlsLaunch p) {
+__global__ void DRS_SLS_PERSIST_BOUNDS k_sls_gather_persist(const SlsLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);            // bar[0], bar[1]
   int32_t* sidx0 = reinterpret_cast<int32_t*>(smem_raw + 32);
