@@ -134,7 +134,7 @@ ACCEL_FLAGS = (
                                          # process fed through a shared-memory ring
     ("accel_host_pack", int, 0),         # host threads that bit-pack the ids of queries carrying
                                          # their own inputs before the copy (0 = ids travel as
-                                         # they are; pays for queries of >= 65,536 lookups)
+                                         # they are; used for queries of >= 1,048,576 lookups)
     ("data_trace_sort_lookups", _T, False),  # --data_generation synthetic: sort the ids inside
                                          # every lookup (the random generator's np.unique does)
 )

@@ -187,7 +187,7 @@ int drs_enqueue_host_packed(drs_engine* e, const float* dense, const uint32_t* c
  * (drs_infer / drs_enqueue_host / drs_submit_host, int32 or int64 ids — the dtype the reference
  * hands run_queues, dlrm_s_caffe2.py:223-226,308) pack the ids of tables with <= 2^24 rows on
  * n host threads into pinned staging, table by table, each table's copy leaving while the next is
- * packed; queries with fewer than "host_pack_min_ids" lookups (default 65,536) go up unpacked.
+ * packed; queries with fewer than "host_pack_min_ids" lookups (default 1,048,576) go up unpacked.
  * Results and the DRS_ERR_INDEX behaviour are those of the unpacked path (a table holding an id
  * that is negative or past 2^bits is uploaded as it came, and the gather raises the enforce).
  * The wire layout is engine-internal (lane-interleaved 512-id blocks, csrc/hostpack.h);
