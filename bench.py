@@ -239,7 +239,8 @@ def load_traffic(config, B, sharded, lanes):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the gather kernel from the
     committed ``ncu --set full`` capture of this same command (profiles/), or None when no
     capture covers this workload."""
-    names = {"rm1": ["r02_gather_rm1_ncu_full_summary.json",
+    names = {"rm1": ["r02z_gather_rm1_ncu_full_summary.json",      # final state of round 2
+                     "r02_gather_rm1_ncu_full_summary.json",
                      "r01f_gather_persist_ncu_full_summary.json"],
              "rm2": ["r02_gather_rm2_ncu_full_summary.json"]}.get(config, [])
     want_B = {"rm1": 16384, "rm2": 4096}.get(config)
