@@ -78,7 +78,7 @@ _SIGNATURES = {
     "drs_sync": (C.c_int, [C.c_void_p]),
     "drs_packed_words": (C.c_int64, [C.c_int64, C.c_int]),
     "drs_pack_ids": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
-    "drs_wire_parse_requests": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+    "drs_wire_parse_requests": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p, C.c_void_p, C.c_int,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                           C.POINTER(C.c_int32)]),
     "drs_wire_emit_responses": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p,

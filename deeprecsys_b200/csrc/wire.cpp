@@ -7,8 +7,9 @@
 //
 //   drs_wire_parse_requests   a buffer of frames read from the request pipe -> fixed-size
 //                             records, as long as each frame is exactly a pickled
-//                             `ServiceRequest` whose fields are int / bool / None (arrival_time:
-//                             float / None); the first frame that is anything else (the final
+//                             `ServiceRequest` (of a module the caller names) whose fields are
+//                             int / bool / None (arrival_time: float / None); the first frame
+//                             that is anything else (the final
 //                             None, a request that carries tensors, an unexpected type) stops
 //                             the parse and is left to pickle.loads;
 //   drs_wire_emit_responses   records -> frames holding pickled `ServiceResponse` objects
@@ -97,14 +98,28 @@ bool value(Cursor& c, Value* v) {
   }
 }
 
+// is (s, len) one of the NUL-separated names of `list` (terminated by an empty name)?
+bool listed(const char* list, const uint8_t* s, int len) {
+  for (const char* m = list; *m; m += std::strlen(m) + 1)
+    if (is(s, len, m)) return true;
+  return false;
+}
+
 // payload = pickle.dumps(ServiceRequest(...)) exactly?  -> record
-bool parse_request(const uint8_t* p, int64_t n, drs_wire_rec* r) {
+bool parse_request(const uint8_t* p, int64_t n, const char* modules, drs_wire_rec* r) {
   Cursor c{p, p + n};
   if (!c.take(OP_PROTO) || !c.have(1) || (*c.p != 4 && *c.p != 5)) return false;
   ++c.p;
-  if (c.take(OP_FRAME)) { if (!c.have(8)) return false; c.p += 8; }
+  if (c.take(OP_FRAME)) {                                      // must frame exactly the rest
+    if (!c.have(8)) return false;
+    uint64_t fl;
+    std::memcpy(&fl, c.p, 8);
+    c.p += 8;
+    if (fl != (uint64_t)(c.end - c.p)) return false;
+  }
   const uint8_t* s; int len;
-  if (!short_str(c, &s, &len)) return false;                   // module (any: the caller's tree)
+  if (!short_str(c, &s, &len)) return false;                   // module: one the caller vouches for
+  if (modules && !listed(modules, s, len)) return false;
   if (!short_str(c, &s, &len) || !is(s, len, "ServiceRequest")) return false;
   if (!c.take(OP_STACK_GLOBAL) || !c.take(OP_MEMOIZE) || !c.take(OP_EMPTY_TUPLE) ||
       !c.take(OP_NEWOBJ) || !c.take(OP_MEMOIZE) || !c.take(OP_EMPTY_DICT) ||
@@ -192,8 +207,9 @@ const char* const kRespFields[12] = {
 
 extern "C" {
 
-int drs_wire_parse_requests(const uint8_t* buf, int64_t len, drs_wire_rec* recs, int max_recs,
-                            int32_t* n_recs, int64_t* consumed, int32_t* stop) {
+int drs_wire_parse_requests(const uint8_t* buf, int64_t len, const char* modules,
+                            drs_wire_rec* recs, int max_recs, int32_t* n_recs, int64_t* consumed,
+                            int32_t* stop) {
   if (!buf || !recs || !n_recs || !consumed || !stop || len < 0 || max_recs < 0)
     return DRS_ERR_INVALID;
   int64_t pos = 0;
@@ -205,7 +221,7 @@ int drs_wire_parse_requests(const uint8_t* buf, int64_t len, drs_wire_rec* recs,
                                  ((uint32_t)buf[pos + 2] << 8) | (uint32_t)buf[pos + 3]);
     if (sz < 0) { *stop = DRS_WIRE_PYTHON; break; }            // > 2 GiB framing: not ours
     if (len - pos - 4 < sz) break;
-    if (!parse_request(buf + pos + 4, sz, &recs[n])) { *stop = DRS_WIRE_PYTHON; break; }
+    if (!parse_request(buf + pos + 4, sz, modules, &recs[n])) { *stop = DRS_WIRE_PYTHON; break; }
     pos += 4 + (int64_t)sz;
     ++n;
   }

@@ -48,8 +48,13 @@ def _class_ops(cls):
 
 
 class WireCodec(object):
-    def __init__(self, response_cls, consumer_id, max_recs=1024):
+    def __init__(self, response_cls, consumer_id, max_recs=1024, request_modules=None):
+        """``request_modules``: module paths a ``ServiceRequest`` frame may name (default: the
+        reference checkout's ``utils.packets`` and this package's); a frame naming any other
+        module goes to ``pickle.loads``, which knows whether that module exists."""
         self.lib = _lib.load()
+        mods = list(request_modules or ("utils.packets", "deeprecsys_b200.utils.packets"))
+        self._modules = b"".join(m.encode("utf-8") + b"\0" for m in mods) + b"\0"
         self.response_cls = response_cls
         self.consumer_id = int(consumer_id)
         self.max_recs = int(max_recs)
@@ -71,7 +76,7 @@ class WireCodec(object):
         """-> (records (a copy), bytes consumed, stop reason)."""
         view = np.frombuffer(buf, dtype=np.uint8)
         _lib.check(self.lib.drs_wire_parse_requests(
-            view.ctypes.data, view.shape[0], self._recs.ctypes.data, self.max_recs,
+            view.ctypes.data, view.shape[0], self._modules, self._recs.ctypes.data, self.max_recs,
             C.byref(self._n), C.byref(self._consumed), C.byref(self._stop)))
         return self._recs[:self._n.value].copy(), self._consumed.value, self._stop.value
 

@@ -318,6 +318,9 @@ int drs_exchange_end(drs_engine* e);
  * 2 None.
  *   drs_wire_parse_requests: decodes the leading frames of buf[0, len) that are exactly a pickled
  *     `ServiceRequest` with int / bool / None fields (arrival_time: float / None) into recs;
+ *     `modules` = the module paths the class may come from, NUL-separated and ended by an empty
+ *     name ("utils.packets\0deeprecsys_b200.utils.packets\0"; NULL = any) — a frame naming
+ *     another module is left to pickle, which knows whether that module exists;
  *     *consumed = bytes of the decoded frames; *stop says why it stopped: NEED_MORE (the rest is
  *     an incomplete frame), FULL (max_recs reached), PYTHON (the next frame is something else —
  *     the final None, a request carrying tensors, an unexpected type: the caller unpickles it).
@@ -335,8 +338,9 @@ typedef struct drs_wire_rec {
   double arrival_time, start_time, end_time;
 } drs_wire_rec;
 enum { DRS_WIRE_NEED_MORE = 0, DRS_WIRE_PYTHON = 1, DRS_WIRE_FULL = 2 };
-int drs_wire_parse_requests(const uint8_t* buf, int64_t len, drs_wire_rec* recs, int max_recs,
-                            int32_t* n_recs, int64_t* consumed, int32_t* stop);
+int drs_wire_parse_requests(const uint8_t* buf, int64_t len, const char* modules,
+                            drs_wire_rec* recs, int max_recs, int32_t* n_recs, int64_t* consumed,
+                            int32_t* stop);
 int drs_wire_emit_responses(const drs_wire_rec* recs, int n, const uint8_t* class_ops,
                             int class_ops_len, const int32_t* field_order, int64_t consumer_id,
                             uint8_t* out, int64_t cap, int64_t* out_len);

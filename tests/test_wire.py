@@ -112,3 +112,80 @@ def test_requests_pickled_from_another_module_path_parse_too():
     r = recs[0]
     assert (r["batch_id"], r["epoch"], r["batch_size"], r["sub_id"], r["total_sub_batches"],
             r["exp_packet"], r["arrival_time"]) == (9, 1, 30, 1, 2, 1, 2.0)
+
+
+# ------------------------------------------------------------------ robustness of the C parser
+class _GuardedBuffer(object):
+    """Bytes placed so that the byte after the last one is an inaccessible page: a parser that
+    reads past the end of its input dies here instead of passing by luck."""
+
+    def __init__(self, max_len):
+        import ctypes
+        import mmap
+        self.page = mmap.PAGESIZE
+        self.pages = (max_len + self.page - 1) // self.page + 1
+        self.map = mmap.mmap(-1, self.pages * self.page)
+        self.base = ctypes.addressof(ctypes.c_char.from_buffer(self.map))
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        guard = self.base + (self.pages - 1) * self.page
+        assert libc.mprotect(ctypes.c_void_p(guard), self.page, 0) == 0      # PROT_NONE
+        self.limit = (self.pages - 1) * self.page
+
+    def place(self, data):
+        start = self.limit - len(data)
+        self.map[start:self.limit] = data
+        return self.base + start
+
+
+_guard = _GuardedBuffer(1 << 16)
+
+
+def _parse_guarded(codec, data):
+    import ctypes as C
+    from deeprecsys_b200 import _lib
+    n, consumed, stop = C.c_int32(), C.c_int64(), C.c_int32()
+    ptr = _guard.place(data) if data else _guard.base
+    _lib.check(codec.lib.drs_wire_parse_requests(ptr, len(data), codec._modules,
+                                                 codec._recs.ctypes.data, codec.max_recs,
+                                                 C.byref(n), C.byref(consumed), C.byref(stop)))
+    return n.value, consumed.value, stop.value
+
+
+@settings(max_examples=400, deadline=None)
+@given(cases=st.lists(request_fields, min_size=1, max_size=4), data=st.data())
+def test_parser_never_reads_past_its_input_and_never_accepts_a_damaged_frame(cases, data):
+    """Truncated, bit-flipped and spliced frames (the bytes of a pipe are not to be trusted): the
+    parser stays inside its buffer (guard page), decodes only whole frames that pickle itself
+    would decode to the same fields, and leaves everything else to the Python path."""
+    codec = wire.WireCodec(ServiceResponse, 1, max_recs=16)
+    frames = [frame(ServiceRequest(**c)) for c in cases]
+    blob = bytearray(b"".join(frames))
+    mode = data.draw(st.sampled_from(["truncate", "flip", "garbage", "intact"]))
+    if mode == "truncate":
+        blob = blob[:data.draw(st.integers(0, len(blob)))]
+    elif mode == "flip":
+        for _ in range(data.draw(st.integers(1, 4))):
+            i = data.draw(st.integers(0, len(blob) - 1))
+            blob[i] ^= 1 << data.draw(st.integers(0, 7))
+    elif mode == "garbage":
+        blob = bytearray(data.draw(st.binary(min_size=0, max_size=300)))
+    n, consumed, stop = _parse_guarded(codec, bytes(blob))
+    assert 0 <= consumed <= len(blob) and 0 <= n <= 16
+    assert stop in (wire.NEED_MORE, wire.PYTHON, wire.FULL)
+    # every frame the parser accepted is one pickle accepts too, with the same fields
+    pos = 0
+    for k in range(n):
+        (sz,) = HDR.unpack_from(blob, pos)
+        obj = pickle.loads(bytes(blob[pos + 4:pos + 4 + sz]))
+        pos += 4 + sz
+        assert type(obj) is ServiceRequest
+        r = codec._recs[k]
+        for i, name in enumerate(("epoch", "batch_id", "batch_size", "sub_id",
+                                  "total_sub_batches", "exp_packet")):
+            v, kind = getattr(obj, name), (int(r["kinds"]) >> (2 * i)) & 3
+            assert kind == (2 if v is None else 1 if isinstance(v, bool) else 0)
+            assert v is None or int(v) == int(r[name])
+        at = obj.arrival_time
+        assert (at is None and (int(r["kinds"]) >> 12) & 3 == 2) or at == r["arrival_time"] \
+            or (at != at and r["arrival_time"] != r["arrival_time"])          # NaN stays NaN
+    assert pos == consumed
