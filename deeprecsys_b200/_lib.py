@@ -20,7 +20,7 @@ MLP_BOT, MLP_TOP, MLP_FINAL, MLP_ATTN_BASE, MLP_TASK_BASE, MLP_RNN_BASE = 0, 1, 
 (STAGE_POOLED, STAGE_BOT, STAGE_INTERACT, STAGE_TOP, STAGE_OUT, STAGE_OFFSETS, STAGE_TASK,
  STAGE_IDS) = range(8)
 SHARD_TABLE, SHARD_ROW = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 SHARD_BLOB_BYTES = 192
 
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}

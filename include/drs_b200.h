@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRS_ABI_VERSION 6
+#define DRS_ABI_VERSION 7
 
 /* status codes */
 enum {

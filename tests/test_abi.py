@@ -45,7 +45,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_binding_covers_the_header(lib):
     assert set(lib.exported_symbols()) == set(_declared())
     handle = lib.load()
-    assert handle.drs_abi_version() == lib.ABI_VERSION == 6
+    assert handle.drs_abi_version() == lib.ABI_VERSION == 7
     assert isinstance(handle.drs_last_error(), bytes)
 
 
