@@ -87,6 +87,9 @@ def parse_args():
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--no_sweep", action="store_true")
     p.add_argument("--no_e2e", action="store_true")
+    p.add_argument("--host_pack_min_ids", type=int, default=1 << 20,
+                   help="e2e: queries with fewer lookups are not packed by the engine (the "
+                        "library default), so the host_pack mode is not timed for them")
     p.add_argument("--no_secondary", action="store_true",
                    help="N=1: skip the rm2 / rm3 / wnd / ncf / din / din254 / mtwnd / dien block")
     p.add_argument("--secondary", type=str, default=None,
@@ -680,6 +683,10 @@ class Workload(object):
         sweep = sorted({max(1, min(8, per_rank // 2)), max(1, min(16, per_rank))}) \
             if int64_too else [max(1, min(8, per_rank // 2))]
         hp = {}
+        if B * T * L < self.opts.host_pack_min_ids:
+            sweep = []                  # below the engine's threshold nothing would be packed
+        else:
+            eng.set_option("host_pack_min_ids", self.opts.host_pack_min_ids)
         for th in sweep:
             eng.set_option("host_pack", th)
             dt, t_enq = self._time_host_steps(steps, *args32)
@@ -687,8 +694,8 @@ class Workload(object):
                       "h2d_bytes_per_step": int(words * 4 + small),
                       "ms_per_step": 1e3 * dt / steps,
                       "enqueue_call_ms_avg": 1e3 * t_enq / steps}
-        best_th = max(hp, key=lambda k: hp[k]["value"])
-        best = hp[best_th] if hp[best_th]["value"] > plain["value"] else plain
+        best_th = max(hp, key=lambda k: hp[k]["value"]) if hp else None
+        best = hp[best_th] if hp and hp[best_th]["value"] > plain["value"] else plain
         e2e = {"value": best["value"], "unit": UNIT,
                "mode": "host_pack" if best is not plain else "plain",
                "h2d_bytes_per_step": best["h2d_bytes_per_step"],
@@ -712,12 +719,14 @@ class Workload(object):
             p64 = (C.c_void_p * T)(*[h64[t].ctypes.data for t in range(T)])
             args64 = (h["den_ptr"], p64, 1, h["len_ptrs"], h["out_ptr"])
             n64 = max(5, steps // 3)
-            th64 = max(sweep)
-            eng.set_option("host_pack", th64)
-            dt, _ = self._time_host_steps(n64, *args64)
-            e2e["int64_ids"] = {"host_pack": {"value": env.world * B * n64 / dt, "unit": UNIT,
-                                              "steps": n64, "host_threads": th64,
-                                              "h2d_bytes_per_step": int(words * 4 + small)}}
+            e2e["int64_ids"] = {}
+            if sweep:
+                th64 = max(sweep)
+                eng.set_option("host_pack", th64)
+                dt, _ = self._time_host_steps(n64, *args64)
+                e2e["int64_ids"]["host_pack"] = {
+                    "value": env.world * B * n64 / dt, "unit": UNIT, "steps": n64,
+                    "host_threads": th64, "h2d_bytes_per_step": int(words * 4 + small)}
             eng.set_option("host_pack", 0)
             dt, _ = self._time_host_steps(n64, *args64)
             e2e["int64_ids"]["plain"] = {"value": env.world * B * n64 / dt, "unit": UNIT,

@@ -42,7 +42,8 @@ def _finish(proc, timeout=900):
 
 
 COMMON = ["--steps", "3", "--warmup", "1", "--batch", "64", "--staged_batches", "2",
-          "--cpu_seconds", "0.2", "--cpu_sample", "32", "--no_system"]
+          "--cpu_seconds", "0.2", "--cpu_sample", "32", "--no_system",
+          "--host_pack_min_ids", "0"]          # (64-sample steps: time the packed mode anyway)
 
 
 def test_single_gpu_line_carries_every_secondary_config():
