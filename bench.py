@@ -680,8 +680,13 @@ class Workload(object):
         words = sum(int(lib.drs_hostpack_words(B * L, id_bits(r))) if id_bits(r) <= 24
                     else B * L for r in spec.table_rows)
         per_rank = max(1, cores // env.world)
-        sweep = sorted({max(1, min(8, per_rank // 2)), max(1, min(16, per_rank))}) \
-            if int64_too else [max(1, min(8, per_rank // 2))]
+        # (B200 box, 16 cores: 3 / 4 / 5 / 6 / 8 / 12 threads -> 20.8 / 22.2 / 22.2 / 21.9 / 21.2 /
+        # 20.0 M inf/s, profiles/r02ad_*: past 4-5 threads the packers only fight the copy
+        # engine for the host's memory)
+        few = max(1, min(4, per_rank // 4 if per_rank >= 8 else per_rank // 2))
+        sweep = sorted({few, max(1, min(8, per_rank // 2))}) if int64_too else [few]
+        if int64_too and os.environ.get("DRS_BENCH_PACK_THREADS"):      # tuning runs: "4,6,8,12"
+            sweep = sorted({int(x) for x in os.environ["DRS_BENCH_PACK_THREADS"].split(",")})
         hp = {}
         if B * T * L < self.opts.host_pack_min_ids:
             sweep = []                  # below the engine's threshold nothing would be packed
