@@ -102,6 +102,29 @@ def test_slices_served_alone_equal_the_rows_of_the_whole_query(rm1, start):
     np.testing.assert_allclose(out, rm1["out"][start:start + n], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("wide", [False, True], ids=["int32", "int64"])
+def test_whole_query_through_the_host_packed_upload_equals_the_staged_one(rm1, wide):
+    """drs_set_option "host_pack": all 10.5 M lookups of the 16,384-sample query travel as 22-bit
+    fields in lane-interleaved blocks (8 host threads, many chunks per table) and are widened on
+    the GPU — same ids, same pooled bits, same scores as the staged int32 path."""
+    spec, eng = rm1["spec"], rm1["eng"]
+    dtype = np.int64 if wide else np.int32
+    ids = [np.ascontiguousarray(rm1["ids"][t], dtype=dtype) for t in range(spec.T)]
+    lengths = [np.ascontiguousarray(rm1["lengths"][t]) for t in range(spec.T)]
+    eng.set_option("host_pack", 8)
+    try:
+        l0 = eng.launch_count()
+        out, _ = eng.infer(np.ascontiguousarray(rm1["dense"]), ids, lengths, B)
+        pooled = eng.fetch_stage(_lib.STAGE_POOLED)
+        assert eng.launch_count() - l0 >= spec.T           # one widening kernel per table ran
+        for t in (0, spec.T - 1):
+            assert np.array_equal(eng.fetch_stage(_lib.STAGE_IDS, t).ravel(), rm1["ids"][t])
+    finally:
+        eng.set_option("host_pack", 0)
+    assert np.array_equal(pooled.view(np.uint32), rm1["pooled"].view(np.uint32))
+    np.testing.assert_allclose(out, rm1["out"], rtol=0, atol=1e-6)
+
+
 def test_sampled_rows_against_the_oracle(rm1):
     spec, L = rm1["spec"], rm1["spec"].L
     pick = np.sort(np.random.RandomState(5).choice(B, size=64, replace=False))
