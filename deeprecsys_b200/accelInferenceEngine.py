@@ -499,8 +499,8 @@ def _serve_records(args, backend, codec, reader, requestQueue, responseQueue, de
     nbatches = int(backend.nbatches)
     max_rows = int(args.max_mini_batch_size)
     coalesce = min(int(coalesce), 32)                      # drs_submit_many: <= 32 requests
-    # int fields of batch_id (index 1) and batch_size (index 2) must be plain ints
-    kind_mask = (3 << 2) | (3 << 4)
+    # batch_id (field 1) and batch_size (field 2) must be numbers (a bool counts, as int(True)
+    # does in the object loop), not None: kind 2 in their two-bit slots of `kinds`
     buf = reader._buf
     inflight = collections.deque()                         # (records, handle, rows)
     st = {"recs": None, "head": 0, "bail": False, "served": 0}
@@ -521,8 +521,10 @@ def _serve_records(args, backend, codec, reader, requestQueue, responseQueue, de
                         release()                          # Queue.get: a free slot per packet
                     recs["start_time"] = time.time()
                     sizes = recs["batch_size"]
+                    kinds = recs["kinds"]
                     ok = ((sizes >= 1) & (sizes <= max_rows) & (recs["batch_id"] >= 0)
-                          & (recs["batch_id"] < nbatches) & ((recs["kinds"] & kind_mask) == 0))
+                          & (recs["batch_id"] < nbatches)
+                          & (((kinds >> 2) & 3) != 2) & (((kinds >> 4) & 3) != 2))
                     st["recs"], st["head"] = recs, 0
                     st["ok"] = ok
                     st["bad"] = np.flatnonzero(~ok)

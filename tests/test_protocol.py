@@ -276,6 +276,7 @@ def test_record_loop_hands_over_to_the_object_loop_and_back_to_nothing(tmp_path,
     reqs[5].batch_size = 0                                 # refused in the record loop
     reqs[6].batch_id = 99                                  # no such staged batch
     reqs[7].batch_size = None
+    reqs[8].batch_size = True                              # int(True) = 1 row, echoed as True
     reqs[30].sub_id, reqs[30].total_sub_batches = None, True
     reqs[60].exp_packet = "yes"                            # -> pickle.loads, object loop from here
     reqs[90].colour = "blue"
@@ -291,6 +292,7 @@ def test_record_loop_hands_over_to_the_object_loop_and_back_to_nothing(tmp_path,
             assert a == b and type(a) is type(b), (q.epoch, name, a, b)
         assert r.consumer_id == 7 and r.queue_start_time <= r.queue_end_time == r.inference_end_time
     assert [by_epoch[e].out_batch_size for e in (5, 6, 7)] == [0, 0, 0]
+    assert by_epoch[8].out_batch_size == 1 and by_epoch[8].batch_size is True
     assert all(by_epoch[e].out_batch_size == reqs[e].batch_size
                for e in range(120) if e not in (5, 6, 7))
     # the first sixty were answered before anything after the hand-over
