@@ -697,7 +697,9 @@ class Workload(object):
             eng.set_option("host_pack_min_ids", self.opts.host_pack_min_ids)
         for th in sweep:
             eng.set_option("host_pack", th)
-            dt, t_enq = self._time_host_steps(steps, *args32)
+            # (two warm-up steps per lane: the first packed step of a lane allocates its pinned
+            # staging and wakes a freshly created pool)
+            dt, t_enq = self._time_host_steps(steps, *args32, warm=6)
             hp[th] = {"value": env.world * B * steps / dt, "unit": UNIT, "host_threads": th,
                       "h2d_bytes_per_step": int(words * 4 + small),
                       "ms_per_step": 1e3 * dt / steps,
