@@ -687,7 +687,7 @@ class Workload(object):
         # 20.0 M inf/s, profiles/r02ad_*: past 4-5 threads the packers only fight the copy
         # engine for the host's memory)
         few = max(1, min(4, per_rank // 4 if per_rank >= 8 else per_rank // 2))
-        sweep = sorted({few, max(1, min(8, per_rank // 2))}) if int64_too else [few]
+        sweep = sorted({few, max(1, min(8, per_rank // 2))})    # (RMC2's id-heavy steps like 8)
         if int64_too and os.environ.get("DRS_BENCH_PACK_THREADS"):      # tuning runs: "4,6,8,12"
             sweep = sorted({int(x) for x in os.environ["DRS_BENCH_PACK_THREADS"].split(",")})
         hp = {}
